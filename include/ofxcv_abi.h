@@ -1,0 +1,176 @@
+/*
+ * ofxcv_abi.h — the drop-in C ABI of the B200-native filter bodies behind openfx-opencv's render actions.
+ *
+ * Every entry point replaces ONE OpenCV call the reference plugins make from their render action
+ * (the reference file:line is cited on each).  Plain C types only: no OFX, OpenCV, CUDA-runtime or torch
+ * types appear in a signature (`ofxcv_stream` is a `cudaStream_t` passed as void*; NULL = the context's
+ * own stream).  Two flavours per op:
+ *   ofxcv_<op>        all image pointers are DEVICE pointers, work is enqueued on `stream`, no sync;
+ *   ofxcv_<op>_host   all image pointers are HOST pointers; the call stages them through pinned memory into
+ *                     HBM once, runs the same kernels, copies the result back and synchronises (this is the
+ *                     call the OFX glue makes when the host did not enable CUDA render).
+ * Return value: 0 (OFXCV_OK) or a negative ofxcv_status.  There is NO CPU fallback anywhere in this library:
+ * without a usable CUDA device `ofxcv_create` returns NULL and every op returns OFXCV_ERR_NO_DEVICE.
+ *
+ * Threading: a context is used by one thread at a time (it owns its workspace, stream and pinned staging);
+ * create one per render thread (the OFX glue keeps a small pool).  Different contexts are fully independent,
+ * so the library is re-entrant as kOfxImageEffectRenderFullySafe needs (VectorGenerator.cpp:108).
+ */
+#ifndef OFXCV_ABI_H
+#define OFXCV_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define OFXCV_API __attribute__((visibility("default")))
+#else
+#define OFXCV_API
+#endif
+
+typedef struct ofxcv_ctx ofxcv_ctx;
+typedef void* ofxcv_stream; /* cudaStream_t */
+
+typedef enum ofxcv_status {
+    OFXCV_OK = 0,
+    OFXCV_ERR_BAD_ARG = -1,   /* NULL pointer, non-positive size, unsupported channel count ... */
+    OFXCV_ERR_NO_DEVICE = -2, /* no CUDA device / context creation failed */
+    OFXCV_ERR_MEMORY = -3,    /* device or pinned allocation failed (maps to kOfxStatErrMemory) */
+    OFXCV_ERR_CUDA = -4,      /* any other CUDA runtime error (maps to kOfxStatFailed) */
+    OFXCV_ERR_UNSUPPORTED = -5
+} ofxcv_status;
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+OFXCV_API int ofxcv_abi_version(void); /* 1 */
+OFXCV_API const char* ofxcv_status_string(int status);
+OFXCV_API int ofxcv_device_count(void);
+/* device < 0: use the calling thread's current CUDA device. */
+OFXCV_API ofxcv_ctx* ofxcv_create(int device);
+OFXCV_API void ofxcv_destroy(ofxcv_ctx* ctx);
+OFXCV_API int ofxcv_device(const ofxcv_ctx* ctx);
+OFXCV_API ofxcv_stream ofxcv_ctx_stream(ofxcv_ctx* ctx);
+OFXCV_API int ofxcv_synchronize(ofxcv_ctx* ctx);
+OFXCV_API const char* ofxcv_last_error(const ofxcv_ctx* ctx); /* text of the last CUDA error seen by ctx */
+/* number of kernel launches issued through this context so far (bench.py's gpu_launches claim) */
+OFXCV_API uint64_t ofxcv_launch_count(const ofxcv_ctx* ctx);
+/* device-time (ms, CUDA events on the launching stream) of the dominant kernel family since the last reset:
+ * family 0 = Farneback iteration kernel, 1 = inpaint fill, 2 = watershed flood.  Returns launches counted. */
+OFXCV_API uint64_t ofxcv_kernel_time_ms(ofxcv_ctx* ctx, int family, double* total_ms);
+OFXCV_API void ofxcv_kernel_time_enable(ofxcv_ctx* ctx, int enable);
+
+/* plain device-memory helpers so that a non-CUDA host language (ctypes, cgo, JNI) can stage frames */
+OFXCV_API void* ofxcv_device_alloc(ofxcv_ctx* ctx, size_t bytes);
+OFXCV_API void ofxcv_device_free(ofxcv_ctx* ctx, void* dptr);
+OFXCV_API void* ofxcv_pinned_alloc(ofxcv_ctx* ctx, size_t bytes);
+OFXCV_API void ofxcv_pinned_free(ofxcv_ctx* ctx, void* hptr);
+OFXCV_API int ofxcv_upload(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, const void* src_host, size_t bytes);
+OFXCV_API int ofxcv_download(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_host, const void* src_dev, size_t bytes);
+OFXCV_API int ofxcv_memset(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, int value, size_t bytes);
+
+/* ---- dense optical flow ----------------------------------------------------------------------------- */
+/* Replaces cv::calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, iters, poly_n,
+ * poly_sigma, flags) as called at /root/reference/VectorGenerator/VectorGenerator.cpp:403
+ * (argument values :391-399; parameter defaults :804,:814,:824,:834).                                     */
+typedef struct ofxcv_fb_params {
+    double pyr_scale;  /* 0.5  (VectorGenerator.cpp:391) */
+    int levels;        /* 3    (:804)  -- runs levels+1 scales, like OpenCV */
+    int winsize;       /* 3    (:395)  -- only 3 is implemented (the value the plugin hard-wires) */
+    int iterations;    /* 15   (:814) */
+    int poly_n;        /* 5    (:824)  -- 1..16 */
+    double poly_sigma; /* 1.1  (:834) */
+    int flags;         /* 0    (:403)  -- OPTFLOW_USE_INITIAL_FLOW / FARNEBACK_GAUSSIAN unsupported */
+} ofxcv_fb_params;
+
+OFXCV_API void ofxcv_fb_default_params(ofxcv_fb_params* p);
+/* number of scales that will run (effective levels + 1) and the algorithmic HBM bytes of one pair
+ * (SURVEY.md section 8d byte model: sum_k n_k*(66+88*I) + 2*W*H per scale). */
+OFXCV_API int ofxcv_farneback_scales(int W, int H, const ofxcv_fb_params* p);
+OFXCV_API double ofxcv_farneback_algorithmic_bytes(int W, int H, const ofxcv_fb_params* p);
+/* algorithmic bytes handled by the iteration-kernel launches alone (88 B per scale-pixel per iteration,
+ * 28 for the last one) -- the numerator of bench.py's roofline for the dominant kernel. */
+OFXCV_API double ofxcv_farneback_iter_bytes(int W, int H, const ofxcv_fb_params* p);
+OFXCV_API size_t ofxcv_farneback_workspace_bytes(int W, int H, const ofxcv_fb_params* p);
+
+/* prev/next: 8-bit gray, `stride` bytes per row; flow: interleaved (dx,dy) float32, `flow_stride` BYTES/row. */
+OFXCV_API int ofxcv_farneback_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, const uint8_t* next,
+                                 ptrdiff_t stride, int W, int H, float* flow, ptrdiff_t flow_stride,
+                                 const ofxcv_fb_params* params);
+OFXCV_API int ofxcv_farneback_u8_host(ofxcv_ctx* ctx, const uint8_t* prev, const uint8_t* next, ptrdiff_t stride,
+                                      int W, int H, float* flow, ptrdiff_t flow_stride,
+                                      const ofxcv_fb_params* params);
+
+/* ---- inpainting ------------------------------------------------------------------------------------- */
+/* Replaces cvInpaint(image0, mask, image1, radius, CV_INPAINT_TELEA) at
+ * /root/reference/opencv2fx/inpaint/inpaint.cpp:311-318 (Telea hard-wired at :311; Navier-Stokes is the
+ * method BASELINE.json config 4 names).  Method values are OpenCV's: cv::INPAINT_NS=0, cv::INPAINT_TELEA=1. */
+#define OFXCV_INPAINT_NS 0
+#define OFXCV_INPAINT_TELEA 1
+/* img/out: `channels` (1 or 3) interleaved u8; mask: u8, non-zero = pixel to inpaint. strides in bytes. */
+OFXCV_API int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* img, ptrdiff_t img_stride,
+                               int channels, const uint8_t* mask, ptrdiff_t mask_stride, uint8_t* out,
+                               ptrdiff_t out_stride, int W, int H, double radius, int method);
+OFXCV_API int ofxcv_inpaint_u8_host(ofxcv_ctx* ctx, const uint8_t* img, ptrdiff_t img_stride, int channels,
+                                    const uint8_t* mask, ptrdiff_t mask_stride, uint8_t* out, ptrdiff_t out_stride,
+                                    int W, int H, double radius, int method);
+OFXCV_API size_t ofxcv_inpaint_workspace_bytes(int W, int H, int channels);
+/* statistics of the last inpaint call on ctx: [0]=hole pixels, [1]=dependency levels (parallel fill waves),
+ * [2]=pixels marched sequentially (not covered by the closed-form first ring), [3]=fill kernel launches */
+OFXCV_API int ofxcv_inpaint_last_stats(const ofxcv_ctx* ctx, int64_t stats[4]);
+
+/* ---- segmentation ----------------------------------------------------------------------------------- */
+/* Replaces the segment plugin's body (cvPyrSegmentation at /root/reference/opencv2fx/segment/segment.cpp:296-302)
+ * by cv::watershed(rgb8, int32 markers) as BASELINE.json config 3 requires.
+ * rgb: 3-channel interleaved u8; markers: int32 in/out (>0 seeds; on return labels >0, -1 ridges + border). */
+OFXCV_API int ofxcv_watershed_u8c3(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb, ptrdiff_t rgb_stride,
+                                   int32_t* markers, ptrdiff_t markers_stride, int W, int H);
+OFXCV_API int ofxcv_watershed_u8c3_host(ofxcv_ctx* ctx, const uint8_t* rgb, ptrdiff_t rgb_stride, int32_t* markers,
+                                        ptrdiff_t markers_stride, int W, int H);
+/* `nframes` independent frames flooded concurrently (frame f at base + f*frame_stride bytes): the exact flood
+ * is latency-bound per frame, so sequence throughput comes from frames in flight. */
+OFXCV_API int ofxcv_watershed_u8c3_batch(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb,
+                                         ptrdiff_t rgb_stride, size_t rgb_frame_stride, int32_t* markers,
+                                         ptrdiff_t markers_stride, size_t markers_frame_stride, int W, int H,
+                                         int nframes);
+OFXCV_API size_t ofxcv_watershed_workspace_bytes(int W, int H, int nframes);
+/* stats of the last call: [0]=queue pops (all frames) */
+OFXCV_API int ofxcv_watershed_last_stats(const ofxcv_ctx* ctx, int64_t stats[4]);
+
+/* ---- staging conversions (the steps either side of the OpenCV call inside the render actions) ------- */
+/* float RGBA/RGB/Alpha (linear) -> Rec.709 luma -> sRGB 8-bit gray, the semantics of
+ * GenericOpenCVPlugin::fetchCVImage8UGrayscale (/root/reference/OpenCV/GenericOpenCVPlugin.cpp:223-265) with
+ * Lut::to_byte_grayscale_nodither (/root/reference/SupportExt/ofxsLut.h:447-486) over the WHOLE row
+ * (SURVEY.md Appendix B1).  ncomp = 4, 3 or 1; src_stride/dst_stride in bytes (src_stride may be negative). */
+OFXCV_API int ofxcv_rgba32f_to_srgb_gray8(ofxcv_ctx* ctx, ofxcv_stream stream, const float* src,
+                                          ptrdiff_t src_stride, int ncomp, uint8_t* dst, ptrdiff_t dst_stride,
+                                          int W, int H);
+/* flow -> selected RGBA channels with the renderScale division: VectorGenerator.cpp:494-519.
+ * chan_sel[c] for c = R,G,B,A: -1 = leave untouched, 0 = flow.x / scale_x, 1 = flow.y / scale_y. */
+OFXCV_API int ofxcv_flow_to_rgba32f(ofxcv_ctx* ctx, ofxcv_stream stream, const float* flow, ptrdiff_t flow_stride,
+                                    float* dst, ptrdiff_t dst_stride, int W, int H, const int chan_sel[4],
+                                    double scale_x, double scale_y);
+/* RGBA8 -> RGB8 + hole mask: cvCvtColor x3 + cvThreshold(BINARY_INV, 0) + cvDilate(3x3, iterations) of
+ * /root/reference/opencv2fx/inpaint/inpaint.cpp:303-309.  mask = 255 where gray(rgb)==0, dilated. */
+OFXCV_API int ofxcv_rgba8_to_rgb8_mask(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgba,
+                                       ptrdiff_t rgba_stride, uint8_t* rgb, ptrdiff_t rgb_stride, uint8_t* mask,
+                                       ptrdiff_t mask_stride, int W, int H, int dilate_iterations);
+/* RGB8 -> RGBA8 with alpha 255: the write-back loop inpaint.cpp:320-358 / segment.cpp:307-323. */
+OFXCV_API int ofxcv_rgb8_to_rgba8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb, ptrdiff_t rgb_stride,
+                                  uint8_t* rgba, ptrdiff_t rgba_stride, int W, int H);
+/* deterministic seed grid for the segment plugin (`seeds` param): n = gx*gy squares of
+ * (2*half+1)^2 pixels labelled 1..n on a regular grid, 0 elsewhere. */
+OFXCV_API int ofxcv_seed_grid(ofxcv_ctx* ctx, ofxcv_stream stream, int32_t* markers, ptrdiff_t markers_stride,
+                              int W, int H, int gx, int gy, int half);
+/* labels -> RGBA8 visualisation: mean colour of each segment (label>0), ridges black; the segment plugin's
+ * output image (cvPyrSegmentation also paints each segment with its mean colour). nlabels = max label. */
+OFXCV_API int ofxcv_labels_to_rgba8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb, ptrdiff_t rgb_stride,
+                                    const int32_t* labels, ptrdiff_t labels_stride, uint8_t* rgba,
+                                    ptrdiff_t rgba_stride, int W, int H, int nlabels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFXCV_ABI_H */

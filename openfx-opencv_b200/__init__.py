@@ -1,0 +1,354 @@
+"""openfx-opencv_b200 — B200-native filter bodies behind openfx-opencv's OFX render actions.
+
+This package is the thin Python host side above the C ABI of ``include/ofxcv_abi.h`` (``libofxcv_b200.so``,
+hand-written sm_100a CUDA).  It exists for the parity tests, the bench and the sequence driver; the
+reference-facing product is the set of ``.ofx`` bundles built from ``ofx/`` which call the same C ABI.
+
+There is NO CPU fallback: importing works anywhere (so that the symbol table can be checked on a CPU box), but
+every compute call raises unless the CUDA library is built and a GPU is present.
+
+The package directory name contains a hyphen (it is the name the build contract asks for), so import it with
+``importlib.import_module("openfx-opencv_b200")`` — ``tests/conftest.py`` and ``bench.py`` do exactly that.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libofxcv_b200.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "ofxcv_abi.h")
+_LIB = None
+
+OK = 0
+INPAINT_NS, INPAINT_TELEA = 0, 1
+
+
+class OfxcvError(RuntimeError):
+    def __init__(self, status, where, detail=""):
+        self.status = status
+        msg = "%s failed: %s (%d)" % (where, _status_string(status), status)
+        if detail:
+            msg += " — " + detail
+        super().__init__(msg)
+
+
+class FbParams(C.Structure):
+    """ofxcv_fb_params (defaults = the reference plugin's: VectorGenerator.cpp:391-399,:804-834)."""
+    _fields_ = [("pyr_scale", C.c_double), ("levels", C.c_int), ("winsize", C.c_int), ("iterations", C.c_int),
+                ("poly_n", C.c_int), ("poly_sigma", C.c_double), ("flags", C.c_int)]
+
+    def __init__(self, pyr_scale=0.5, levels=3, winsize=3, iterations=15, poly_n=5, poly_sigma=1.1, flags=0):
+        super().__init__(pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags)
+
+
+def build(force=False):
+    """Compile libofxcv_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    import subprocess
+    csrc = os.path.join(_HERE, "csrc")
+    if force:
+        subprocess.check_call(["make", "-C", csrc, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", csrc, "-j4"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    """The loaded C-ABI library.  Fails loudly when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libofxcv_b200.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i, sz, pd, d = C.c_void_p, C.c_int, C.c_size_t, C.c_ssize_t, C.c_double
+    fbp = C.POINTER(FbParams)
+    sigs = {
+        "ofxcv_abi_version": (i, []),
+        "ofxcv_status_string": (C.c_char_p, [i]),
+        "ofxcv_device_count": (i, []),
+        "ofxcv_create": (vp, [i]),
+        "ofxcv_destroy": (None, [vp]),
+        "ofxcv_device": (i, [vp]),
+        "ofxcv_ctx_stream": (vp, [vp]),
+        "ofxcv_synchronize": (i, [vp]),
+        "ofxcv_last_error": (C.c_char_p, [vp]),
+        "ofxcv_launch_count": (C.c_uint64, [vp]),
+        "ofxcv_kernel_time_ms": (C.c_uint64, [vp, i, C.POINTER(C.c_double)]),
+        "ofxcv_kernel_time_enable": (None, [vp, i]),
+        "ofxcv_device_alloc": (vp, [vp, sz]),
+        "ofxcv_device_free": (None, [vp, vp]),
+        "ofxcv_pinned_alloc": (vp, [vp, sz]),
+        "ofxcv_pinned_free": (None, [vp, vp]),
+        "ofxcv_upload": (i, [vp, vp, vp, vp, sz]),
+        "ofxcv_download": (i, [vp, vp, vp, vp, sz]),
+        "ofxcv_memset": (i, [vp, vp, vp, i, sz]),
+        "ofxcv_fb_default_params": (None, [fbp]),
+        "ofxcv_farneback_scales": (i, [i, i, fbp]),
+        "ofxcv_farneback_algorithmic_bytes": (d, [i, i, fbp]),
+        "ofxcv_farneback_iter_bytes": (d, [i, i, fbp]),
+        "ofxcv_farneback_workspace_bytes": (sz, [i, i, fbp]),
+        "ofxcv_farneback_u8": (i, [vp, vp, vp, vp, pd, i, i, vp, pd, fbp]),
+        "ofxcv_farneback_u8_host": (i, [vp, vp, vp, pd, i, i, vp, pd, fbp]),
+        "ofxcv_inpaint_u8": (i, [vp, vp, vp, pd, i, vp, pd, vp, pd, i, i, d, i]),
+        "ofxcv_inpaint_u8_host": (i, [vp, vp, pd, i, vp, pd, vp, pd, i, i, d, i]),
+        "ofxcv_inpaint_workspace_bytes": (sz, [i, i, i]),
+        "ofxcv_inpaint_last_stats": (i, [vp, C.POINTER(C.c_int64)]),
+        "ofxcv_watershed_u8c3": (i, [vp, vp, vp, pd, vp, pd, i, i]),
+        "ofxcv_watershed_u8c3_host": (i, [vp, vp, pd, vp, pd, i, i]),
+        "ofxcv_watershed_u8c3_batch": (i, [vp, vp, vp, pd, sz, vp, pd, sz, i, i, i]),
+        "ofxcv_watershed_workspace_bytes": (sz, [i, i, i]),
+        "ofxcv_watershed_last_stats": (i, [vp, C.POINTER(C.c_int64)]),
+        "ofxcv_rgba32f_to_srgb_gray8": (i, [vp, vp, vp, pd, i, vp, pd, i, i]),
+        "ofxcv_flow_to_rgba32f": (i, [vp, vp, vp, pd, vp, pd, i, i, C.POINTER(C.c_int), d, d]),
+        "ofxcv_rgba8_to_rgb8_mask": (i, [vp, vp, vp, pd, vp, pd, vp, pd, i, i, i]),
+        "ofxcv_rgb8_to_rgba8": (i, [vp, vp, vp, pd, vp, pd, i, i]),
+        "ofxcv_seed_grid": (i, [vp, vp, vp, pd, i, i, i, i, i]),
+        "ofxcv_labels_to_rgba8": (i, [vp, vp, vp, pd, vp, pd, vp, pd, i, i, i]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._ofxcv_sigs = sigs
+    _LIB = L
+    return L
+
+
+def declared_symbols():
+    """Every OFXCV_API function name declared in include/ofxcv_abi.h."""
+    import re
+    text = open(INCLUDE).read()
+    return sorted(set(re.findall(r"OFXCV_API[^;(]*?\b(ofxcv_[a-z0-9_]+)\s*\(", text)))
+
+
+def _status_string(st):
+    try:
+        return lib().ofxcv_status_string(st).decode()
+    except Exception:
+        return "status"
+
+
+def _hp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceBuffer:
+    """A device allocation owned through the C ABI (no torch needed)."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        self.ptr = lib().ofxcv_device_alloc(ctx.h, self.nbytes)
+        if not self.ptr:
+            raise OfxcvError(-3, "ofxcv_device_alloc", ctx.last_error())
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        ctx = self.ctx
+        ctx._check(lib().ofxcv_upload(ctx.h, None, self.ptr, _hp(arr), arr.nbytes), "ofxcv_upload")
+        ctx.synchronize()
+        return self
+
+    def download(self, shape, dtype):
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        ctx = self.ctx
+        ctx._check(lib().ofxcv_download(ctx.h, None, _hp(out), self.ptr, out.nbytes), "ofxcv_download")
+        ctx.synchronize()
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().ofxcv_device_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """ofxcv_ctx: one per host thread; owns a stream, the workspaces and the pinned staging buffers."""
+
+    def __init__(self, device=-1):
+        L = lib()
+        if L.ofxcv_device_count() <= 0:
+            raise OfxcvError(-2, "ofxcv_create", "no CUDA device visible; this library has no CPU fallback")
+        self.h = L.ofxcv_create(int(device))
+        if not self.h:
+            raise OfxcvError(-2, "ofxcv_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ofxcv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def last_error(self):
+        return lib().ofxcv_last_error(self.h).decode()
+
+    def _check(self, st, where):
+        if st != OK:
+            raise OfxcvError(st, where, self.last_error())
+
+    def synchronize(self):
+        self._check(lib().ofxcv_synchronize(self.h), "ofxcv_synchronize")
+
+    def stream(self):
+        return lib().ofxcv_ctx_stream(self.h)
+
+    def launch_count(self):
+        return int(lib().ofxcv_launch_count(self.h))
+
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        return DeviceBuffer(self, max(arr.nbytes, 1)).upload(arr)
+
+    def timing(self, enable):
+        lib().ofxcv_kernel_time_enable(self.h, 1 if enable else 0)
+
+    def kernel_time_ms(self, family):
+        ms = C.c_double(0)
+        n = lib().ofxcv_kernel_time_ms(self.h, family, C.byref(ms))
+        return int(n), float(ms.value)
+
+    # ---- host-buffer entry points (what the OFX glue calls for host-memory clips) ----------------------
+    def farneback(self, prev, nxt, params=None):
+        """prev, nxt: HxW uint8 (numpy, host).  Returns HxWx2 float32 flow (cv2.calcOpticalFlowFarneback layout)."""
+        params = params or FbParams()
+        prev = np.ascontiguousarray(prev, np.uint8)
+        nxt = np.ascontiguousarray(nxt, np.uint8)
+        if prev.ndim != 2 or prev.shape != nxt.shape:
+            raise ValueError("prev/next must be equal-shape HxW uint8")
+        h, w = prev.shape
+        flow = np.empty((h, w, 2), np.float32)
+        st = lib().ofxcv_farneback_u8_host(self.h, _hp(prev), _hp(nxt), w, w, h, _hp(flow), w * 8, C.byref(params))
+        self._check(st, "ofxcv_farneback_u8_host")
+        return flow
+
+    def inpaint(self, img, mask, radius, method):
+        img = np.ascontiguousarray(img, np.uint8)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        cn = 1 if img.ndim == 2 else img.shape[2]
+        h, w = mask.shape
+        if img.shape[:2] != (h, w) or cn not in (1, 3):
+            raise ValueError("img must be HxW or HxWx3 uint8 matching the mask")
+        out = np.empty_like(img)
+        st = lib().ofxcv_inpaint_u8_host(self.h, _hp(img), w * cn, cn, _hp(mask), w, _hp(out), w * cn, w, h, float(radius), int(method))
+        self._check(st, "ofxcv_inpaint_u8_host")
+        return out
+
+    def inpaint_stats(self):
+        s = (C.c_int64 * 4)()
+        self._check(lib().ofxcv_inpaint_last_stats(self.h, s), "ofxcv_inpaint_last_stats")
+        return dict(hole_pixels=s[0], levels=s[1], sequential_pixels=s[2], fill_launches=s[3])
+
+    def watershed(self, rgb, markers):
+        """rgb HxWx3 uint8, markers HxW int32 -> new label map (cv2.watershed semantics; input not modified)."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        m = np.array(markers, np.int32, copy=True, order="C")
+        h, w = m.shape
+        if rgb.shape != (h, w, 3):
+            raise ValueError("rgb must be HxWx3 uint8 matching the markers")
+        st = lib().ofxcv_watershed_u8c3_host(self.h, _hp(rgb), w * 3, _hp(m), w * 4, w, h)
+        self._check(st, "ofxcv_watershed_u8c3_host")
+        return m
+
+    def watershed_stats(self):
+        s = (C.c_int64 * 4)()
+        self._check(lib().ofxcv_watershed_last_stats(self.h, s), "ofxcv_watershed_last_stats")
+        return dict(pops=s[0], frames=s[1])
+
+    # ---- device-pointer entry points (frames already resident in HBM) ------------------------------------
+    def farneback_dev(self, prev_d, next_d, w, h, flow_d, params=None, stride=None, flow_stride=None, stream=None):
+        params = params or FbParams()
+        st = lib().ofxcv_farneback_u8(self.h, stream, prev_d, next_d, stride or w, w, h, flow_d, flow_stride or w * 8, C.byref(params))
+        self._check(st, "ofxcv_farneback_u8")
+
+    def inpaint_dev(self, img_d, cn, mask_d, out_d, w, h, radius, method, stream=None):
+        st = lib().ofxcv_inpaint_u8(self.h, stream, img_d, w * cn, cn, mask_d, w, out_d, w * cn, w, h, float(radius), int(method))
+        self._check(st, "ofxcv_inpaint_u8")
+
+    def watershed_dev(self, rgb_d, markers_d, w, h, nframes=1, stream=None):
+        st = lib().ofxcv_watershed_u8c3_batch(self.h, stream, rgb_d, w * 3, w * h * 3, markers_d, w * 4, w * h * 4, w, h, nframes)
+        self._check(st, "ofxcv_watershed_u8c3_batch")
+
+    # ---- staging conversions ---------------------------------------------------------------------------
+    def rgba32f_to_srgb_gray8(self, img):
+        img = np.ascontiguousarray(img, np.float32)
+        h, w = img.shape[:2]
+        nc = 1 if img.ndim == 2 else img.shape[2]
+        src = self.to_device(img)
+        dst = self.alloc(w * h)
+        self._check(lib().ofxcv_rgba32f_to_srgb_gray8(self.h, None, src.ptr, w * nc * 4, nc, dst.ptr, w, w, h), "ofxcv_rgba32f_to_srgb_gray8")
+        return dst.download((h, w), np.uint8)
+
+    def flow_to_rgba32f(self, flow, dst, chan_sel, scale_x=1.0, scale_y=1.0):
+        flow = np.ascontiguousarray(flow, np.float32)
+        dst = np.ascontiguousarray(dst, np.float32)
+        h, w = flow.shape[:2]
+        fd, dd = self.to_device(flow), self.to_device(dst)
+        sel = (C.c_int * 4)(*chan_sel)
+        self._check(lib().ofxcv_flow_to_rgba32f(self.h, None, fd.ptr, w * 8, dd.ptr, w * 16, w, h, sel, scale_x, scale_y), "ofxcv_flow_to_rgba32f")
+        return dd.download((h, w, 4), np.float32)
+
+    def rgba8_to_rgb8_mask(self, rgba, dilate_iterations=0):
+        rgba = np.ascontiguousarray(rgba, np.uint8)
+        h, w = rgba.shape[:2]
+        src = self.to_device(rgba)
+        rgb, mask = self.alloc(w * h * 3), self.alloc(w * h)
+        self._check(lib().ofxcv_rgba8_to_rgb8_mask(self.h, None, src.ptr, w * 4, rgb.ptr, w * 3, mask.ptr, w, w, h, int(dilate_iterations)),
+                    "ofxcv_rgba8_to_rgb8_mask")
+        return rgb.download((h, w, 3), np.uint8), mask.download((h, w), np.uint8)
+
+    def rgb8_to_rgba8(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        h, w = rgb.shape[:2]
+        src, dst = self.to_device(rgb), self.alloc(w * h * 4)
+        self._check(lib().ofxcv_rgb8_to_rgba8(self.h, None, src.ptr, w * 3, dst.ptr, w * 4, w, h), "ofxcv_rgb8_to_rgba8")
+        return dst.download((h, w, 4), np.uint8)
+
+    def seed_grid(self, w, h, gx, gy, half):
+        dst = self.alloc(w * h * 4)
+        self._check(lib().ofxcv_seed_grid(self.h, None, dst.ptr, w * 4, w, h, gx, gy, half), "ofxcv_seed_grid")
+        return dst.download((h, w), np.int32)
+
+    def labels_to_rgba8(self, rgb, labels, nlabels):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        labels = np.ascontiguousarray(labels, np.int32)
+        h, w = labels.shape
+        r, l, o = self.to_device(rgb), self.to_device(labels), self.alloc(w * h * 4)
+        self._check(lib().ofxcv_labels_to_rgba8(self.h, None, r.ptr, w * 3, l.ptr, w * 4, o.ptr, w * 4, w, h, int(nlabels)), "ofxcv_labels_to_rgba8")
+        return o.download((h, w, 4), np.uint8)
+
+
+def farneback_algorithmic_bytes(w, h, params=None):
+    params = params or FbParams()
+    return float(lib().ofxcv_farneback_algorithmic_bytes(w, h, C.byref(params)))
+
+
+def farneback_iter_bytes(w, h, params=None):
+    params = params or FbParams()
+    return float(lib().ofxcv_farneback_iter_bytes(w, h, C.byref(params)))
+
+
+def farneback_scales(w, h, params=None):
+    params = params or FbParams()
+    return int(lib().ofxcv_farneback_scales(w, h, C.byref(params)))

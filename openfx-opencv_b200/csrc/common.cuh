@@ -1,0 +1,107 @@
+// Internal to libofxcv_b200.so: the context object and small helpers shared by the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ofxcv_abi.h"
+
+struct ofxcv_buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct ofxcv_timed_launch {
+    cudaEvent_t a, b;
+};
+
+struct ofxcv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;  // owned
+    int num_sms = 148;
+    std::string last_error;
+    uint64_t launches = 0;
+    // named device workspaces, grown on demand, reused between calls
+    ofxcv_buf ws[32];
+    // pinned host staging for the *_host entry points
+    ofxcv_buf pin[4];
+    // per-family kernel timing (bench.py roofline numerator): events recorded on the launching stream
+    bool timing = false;
+    std::vector<ofxcv_timed_launch> timed[3];
+    std::vector<ofxcv_timed_launch> event_pool;
+    double timed_ms[3] = {0, 0, 0};
+    uint64_t timed_n[3] = {0, 0, 0};
+    int64_t inpaint_stats[4] = {0, 0, 0, 0};
+    int64_t watershed_stats[4] = {0, 0, 0, 0};
+};
+
+int ofxcv_fail(ofxcv_ctx* ctx, cudaError_t e, const char* what);
+void* ofxcv_ws(ofxcv_ctx* ctx, int slot, size_t bytes);    // device workspace slot (nullptr on OOM)
+void* ofxcv_pin(ofxcv_ctx* ctx, int slot, size_t bytes);   // pinned host slot
+void ofxcv_time_begin(ofxcv_ctx* ctx, int family, cudaStream_t s);
+void ofxcv_time_end(ofxcv_ctx* ctx, int family, cudaStream_t s);
+
+#define OFXCV_CUDA(ctx, call)                                         \
+    do {                                                              \
+        cudaError_t _e = (call);                                      \
+        if (_e != cudaSuccess) return ofxcv_fail((ctx), _e, #call);   \
+    } while (0)
+
+#define OFXCV_LAUNCH_CHECK(ctx)                                              \
+    do {                                                                     \
+        (ctx)->launches++;                                                   \
+        cudaError_t _e = cudaPeekAtLastError();                              \
+        if (_e != cudaSuccess) return ofxcv_fail((ctx), _e, "kernel launch"); \
+    } while (0)
+
+struct ofxcv_device_guard {
+    int prev = -1;
+    explicit ofxcv_device_guard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~ofxcv_device_guard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static inline int ofxcv_div_up(int a, int b) { return (a + b - 1) / b; }
+
+// workspace slot numbering
+enum {
+    WS_FB_TMP = 0,   // row-blurred samples
+    WS_FB_I0,        // pyramid image 0 at the current scale
+    WS_FB_I1,
+    WS_FB_R0Q,       // polynomial expansion of image 0: channels 0..3 (float4 per pixel)
+    WS_FB_R0S,       // channel 4
+    WS_FB_R1Q,
+    WS_FB_R1S,
+    WS_FB_MAQ,       // matrix field ping
+    WS_FB_MAS,
+    WS_FB_MBQ,       // matrix field pong
+    WS_FB_MBS,
+    WS_FB_FLOWA,     // flow of the previous / current scale
+    WS_FB_FLOWB,
+    WS_STAGE_IN0,    // *_host staging on the device
+    WS_STAGE_IN1,
+    WS_STAGE_OUT,
+    WS_INP_A,
+    WS_INP_B,
+    WS_INP_C,
+    WS_INP_D,
+    WS_WS_NEXT,
+    WS_MISC0,
+    WS_MISC1,
+    WS_MISC2,
+    WS_LUT,      // sRGB hipart table of the staging conversion
+    WS_INP_E,
+    WS_INP_F,
+    WS_INP_G,
+    WS_INP_H,
+    WS_COUNT
+};
+static_assert(WS_COUNT <= 32, "workspace slots");

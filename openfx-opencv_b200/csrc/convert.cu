@@ -1,0 +1,297 @@
+// Staging conversions either side of the filter bodies.
+// All are single-pass HBM-bound element-wise kernels.
+#include <math.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+// ---- the sRGB 16-bit-hipart -> uint8xx table of SupportExt's Lut (built on the host exactly like
+// Lut::fillTables, /root/reference/SupportExt/ofxsLut.h:171-190 with to_func_srgb :671-679, from_func_srgb
+// :660-668, index_to_float ofxsLut.cpp:88-119, floatToInt<0xff01> ofxsLut.h:57-68) ---------------------------
+float to_srgb(float v)
+{
+    if (v < 0.0031308f) return (v < 0.0f) ? 0.0f : v * 12.92f;
+    return 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+}
+float from_srgb(float v)
+{
+    if (v < 0.04045f) return (v < 0.0f) ? 0.0f : v * (1.0f / 12.92f);
+    return powf((v + 0.055f) * (1.0f / 1.055f), 2.4f);
+}
+float index_to_float(unsigned short i)
+{
+    if ((i < 0x80) || ((i >= 0x8000) && (i < 0x8080))) return 0;
+    if ((i >= 0x7f80) && (i < 0x8000)) return 3.402823466e+38f;
+    if (i >= 0xff80) return -3.402823466e+38f;
+    uint32_t bits = ((uint32_t)i << 16) | 0x8000u;
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+int float_to_ff01(float value)
+{
+    if (value <= 0) return 0;
+    if (value >= 1.) return 0xff00;
+    return (int)(value * 0xff00 + 0.5);  // float product, double add, truncation (as the reference's template)
+}
+
+std::once_flag g_lut_once;
+uint16_t g_lut[0x10000];
+
+void build_lut()
+{
+    for (int i = 0; i < 0x10000; ++i) g_lut[i] = (uint16_t)float_to_ff01(to_srgb(index_to_float((unsigned short)i)));
+    for (int b = 0; b < 256; ++b) {
+        float f = from_srgb(b / (float)255);
+        uint32_t bits;
+        memcpy(&bits, &f, 4);
+        g_lut[bits >> 16] = (uint16_t)(b << 8);
+    }
+}
+
+__global__ void __launch_bounds__(256) cv_luma_srgb8(const char* __restrict__ src, ptrdiff_t src_stride, int ncomp,
+                                                     uint8_t* __restrict__ dst, ptrdiff_t dst_stride, int W, int H,
+                                                     const uint16_t* __restrict__ lut)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    const float* row = (const float*)(src + (ptrdiff_t)y * src_stride);
+    float l;
+    if (ncomp == 4) {
+        float4 p = reinterpret_cast<const float4*>(row)[x];
+        l = (float)__dadd_rn(__dadd_rn(__dmul_rn(0.2126, (double)p.x), __dmul_rn(0.7152, (double)p.y)), __dmul_rn(0.0722, (double)p.z));
+    } else if (ncomp == 3) {
+        const float* p = row + (size_t)x * 3;
+        l = (float)__dadd_rn(__dadd_rn(__dmul_rn(0.2126, (double)p[0]), __dmul_rn(0.7152, (double)p[1])), __dmul_rn(0.0722, (double)p[2]));
+    } else {
+        l = row[x];
+    }
+    unsigned hi = __float_as_uint(l) >> 16;
+    dst[(size_t)y * dst_stride + x] = (uint8_t)((lut[hi] + 0x80) >> 8);
+}
+
+__global__ void __launch_bounds__(256) cv_flow_to_rgba(const char* __restrict__ flow, ptrdiff_t flow_stride,
+                                                       char* __restrict__ dst, ptrdiff_t dst_stride, int W, int H, int s0,
+                                                       int s1, int s2, int s3, double sx, double sy)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    const float* f = (const float*)(flow + (ptrdiff_t)y * flow_stride) + 2 * (size_t)x;
+    float* d = (float*)(dst + (ptrdiff_t)y * dst_stride) + 4 * (size_t)x;
+    // dstPix[x*4+c] = flow[x*2+coord] / renderScale.{x|y}: float / double -> double division, stored as float
+    float vx = (float)__ddiv_rn((double)f[0], sx), vy = (float)__ddiv_rn((double)f[1], sy);
+    if (s0 >= 0) d[0] = s0 ? vy : vx;
+    if (s1 >= 0) d[1] = s1 ? vy : vx;
+    if (s2 >= 0) d[2] = s2 ? vy : vx;
+    if (s3 >= 0) d[3] = s3 ? vy : vx;
+}
+
+// RGBA8 -> RGB8 and the un-dilated hole mask (cvCvtColor RGBA2GRAY fixed point, then THRESH_BINARY_INV at 0)
+__global__ void __launch_bounds__(256) cv_rgba_split(const uint8_t* __restrict__ rgba, ptrdiff_t rgba_stride,
+                                                     uint8_t* __restrict__ rgb, ptrdiff_t rgb_stride,
+                                                     uint8_t* __restrict__ mask, ptrdiff_t mask_stride, int W, int H)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    const uint8_t* p = rgba + (size_t)y * rgba_stride + 4 * (size_t)x;
+    int r = p[0], g = p[1], b = p[2];
+    uint8_t* q = rgb + (size_t)y * rgb_stride + 3 * (size_t)x;
+    q[0] = (uint8_t)r; q[1] = (uint8_t)g; q[2] = (uint8_t)b;
+    int gray = (9798 * r + 19235 * g + 3735 * b + 16384) >> 15;
+    mask[(size_t)y * mask_stride + x] = gray == 0 ? 255 : 0;
+}
+
+// n successive 3x3 rect dilations == one (2n+1)^2 rect dilation (constant border = not set)
+__global__ void __launch_bounds__(256) cv_dilate_rows(const uint8_t* __restrict__ in, ptrdiff_t is, uint8_t* __restrict__ out,
+                                                      ptrdiff_t os, int W, int H, int n)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    const uint8_t* row = in + (size_t)y * is;
+    uint8_t v = 0;
+    for (int l = max(x - n, 0); l <= min(x + n, W - 1); l++) v |= row[l];
+    out[(size_t)y * os + x] = v;
+}
+__global__ void __launch_bounds__(256) cv_dilate_cols(const uint8_t* __restrict__ in, ptrdiff_t is, uint8_t* __restrict__ out,
+                                                      ptrdiff_t os, int W, int H, int n)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    uint8_t v = 0;
+    for (int k = max(y - n, 0); k <= min(y + n, H - 1); k++) v |= in[(size_t)k * is + x];
+    out[(size_t)y * os + x] = v;
+}
+
+__global__ void __launch_bounds__(256) cv_rgb_to_rgba(const uint8_t* __restrict__ rgb, ptrdiff_t rgb_stride,
+                                                      uint8_t* __restrict__ rgba, ptrdiff_t rgba_stride, int W, int H)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    const uint8_t* p = rgb + (size_t)y * rgb_stride + 3 * (size_t)x;
+    uint8_t* q = rgba + (size_t)y * rgba_stride + 4 * (size_t)x;
+    q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; q[3] = 255;
+}
+
+__global__ void __launch_bounds__(256) cv_seed_grid(int32_t* __restrict__ m, ptrdiff_t ms, int W, int H, int gx, int gy, int half)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    // seed (i,j) is centred at ((2i+1)W/(2gx), (2j+1)H/(2gy))
+    int i = min((int)(((long)x * gx) / W), gx - 1), j = min((int)(((long)y * gy) / H), gy - 1);
+    int cx = (int)(((long)(2 * i + 1) * W) / (2 * gx)), cy = (int)(((long)(2 * j + 1) * H) / (2 * gy));
+    int lab = 0;
+    if (abs(x - cx) <= half && abs(y - cy) <= half) lab = j * gx + i + 1;
+    m[(size_t)y * ms + x] = lab;
+}
+
+// per-label colour sums (u32 x3 + count) by atomics, then paint
+__global__ void __launch_bounds__(256) cv_label_sums(const uint8_t* __restrict__ rgb, ptrdiff_t rgb_stride,
+                                                     const int32_t* __restrict__ lab, ptrdiff_t ls, int W, int H, int nlabels,
+                                                     unsigned long long* __restrict__ sums)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    int l = lab[(size_t)y * ls + x];
+    if (l <= 0 || l > nlabels) return;
+    const uint8_t* p = rgb + (size_t)y * rgb_stride + 3 * (size_t)x;
+    unsigned long long* s = sums + (size_t)l * 4;
+    atomicAdd(s + 0, (unsigned long long)p[0]);
+    atomicAdd(s + 1, (unsigned long long)p[1]);
+    atomicAdd(s + 2, (unsigned long long)p[2]);
+    atomicAdd(s + 3, 1ull);
+}
+__global__ void __launch_bounds__(256) cv_label_paint(const int32_t* __restrict__ lab, ptrdiff_t ls, uint8_t* __restrict__ rgba,
+                                                      ptrdiff_t rgba_stride, int W, int H, int nlabels,
+                                                      const unsigned long long* __restrict__ sums)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    int l = lab[(size_t)y * ls + x];
+    uint8_t* q = rgba + (size_t)y * rgba_stride + 4 * (size_t)x;
+    uint8_t r = 0, g = 0, b = 0;
+    if (l > 0 && l <= nlabels) {
+        const unsigned long long* s = sums + (size_t)l * 4;
+        unsigned long long n = s[3];
+        if (n) {
+            r = (uint8_t)((s[0] + n / 2) / n);
+            g = (uint8_t)((s[1] + n / 2) / n);
+            b = (uint8_t)((s[2] + n / 2) / n);
+        }
+    }
+    q[0] = r; q[1] = g; q[2] = b; q[3] = 255;
+}
+
+}  // namespace
+
+extern "C" {
+
+static cudaStream_t pick(ofxcv_ctx* ctx, ofxcv_stream s) { return s ? (cudaStream_t)s : ctx->stream; }
+
+int ofxcv_rgba32f_to_srgb_gray8(ofxcv_ctx* ctx, ofxcv_stream stream, const float* src, ptrdiff_t src_stride, int ncomp,
+                                uint8_t* dst, ptrdiff_t dst_stride, int W, int H)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!src || !dst || W <= 0 || H <= 0 || (ncomp != 1 && ncomp != 3 && ncomp != 4) || dst_stride < W) return OFXCV_ERR_BAD_ARG;
+    if (ncomp == 4 && (((uintptr_t)src | (size_t)(src_stride < 0 ? -src_stride : src_stride)) & 15)) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    cudaStream_t s = pick(ctx, stream);
+    std::call_once(g_lut_once, build_lut);
+    uint16_t* dl = (uint16_t*)ctx->ws[WS_LUT].p;
+    if (!dl) {
+        dl = (uint16_t*)ofxcv_ws(ctx, WS_LUT, sizeof(g_lut));
+        if (!dl) return OFXCV_ERR_MEMORY;
+        OFXCV_CUDA(ctx, cudaMemcpyAsync(dl, g_lut, sizeof(g_lut), cudaMemcpyHostToDevice, s));
+    }
+    cv_luma_srgb8<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>((const char*)src, src_stride, ncomp, dst, dst_stride, W, H, dl);
+    OFXCV_LAUNCH_CHECK(ctx);
+    return OFXCV_OK;
+}
+
+int ofxcv_flow_to_rgba32f(ofxcv_ctx* ctx, ofxcv_stream stream, const float* flow, ptrdiff_t flow_stride, float* dst,
+                          ptrdiff_t dst_stride, int W, int H, const int chan_sel[4], double scale_x, double scale_y)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!flow || !dst || !chan_sel || W <= 0 || H <= 0) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    cv_flow_to_rgba<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, pick(ctx, stream)>>>((const char*)flow, flow_stride, (char*)dst, dst_stride, W,
+                                                                                  H, chan_sel[0], chan_sel[1], chan_sel[2],
+                                                                                  chan_sel[3], scale_x, scale_y);
+    OFXCV_LAUNCH_CHECK(ctx);
+    return OFXCV_OK;
+}
+
+int ofxcv_rgba8_to_rgb8_mask(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgba, ptrdiff_t rgba_stride, uint8_t* rgb,
+                             ptrdiff_t rgb_stride, uint8_t* mask, ptrdiff_t mask_stride, int W, int H, int dilate_iterations)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!rgba || !rgb || !mask || W <= 0 || H <= 0) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    cudaStream_t s = pick(ctx, stream);
+    dim3 grid(ofxcv_div_up(W, 256), H);
+    cv_rgba_split<<<grid, 256, 0, s>>>(rgba, rgba_stride, rgb, rgb_stride, mask, mask_stride, W, H);
+    OFXCV_LAUNCH_CHECK(ctx);
+    if (dilate_iterations > 0) {
+        uint8_t* tmp = (uint8_t*)ofxcv_ws(ctx, WS_MISC0, (size_t)W * H);
+        if (!tmp) return OFXCV_ERR_MEMORY;
+        cv_dilate_rows<<<grid, 256, 0, s>>>(mask, mask_stride, tmp, W, W, H, dilate_iterations);
+        OFXCV_LAUNCH_CHECK(ctx);
+        cv_dilate_cols<<<grid, 256, 0, s>>>(tmp, W, mask, mask_stride, W, H, dilate_iterations);
+        OFXCV_LAUNCH_CHECK(ctx);
+    }
+    return OFXCV_OK;
+}
+
+int ofxcv_rgb8_to_rgba8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb, ptrdiff_t rgb_stride, uint8_t* rgba,
+                        ptrdiff_t rgba_stride, int W, int H)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!rgb || !rgba || W <= 0 || H <= 0) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    cv_rgb_to_rgba<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, pick(ctx, stream)>>>(rgb, rgb_stride, rgba, rgba_stride, W, H);
+    OFXCV_LAUNCH_CHECK(ctx);
+    return OFXCV_OK;
+}
+
+int ofxcv_seed_grid(ofxcv_ctx* ctx, ofxcv_stream stream, int32_t* markers, ptrdiff_t markers_stride, int W, int H, int gx, int gy,
+                    int half)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!markers || W <= 0 || H <= 0 || gx < 1 || gy < 1 || half < 0 || (markers_stride & 3)) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    cv_seed_grid<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, pick(ctx, stream)>>>(markers, markers_stride / 4, W, H, gx, gy, half);
+    OFXCV_LAUNCH_CHECK(ctx);
+    return OFXCV_OK;
+}
+
+int ofxcv_labels_to_rgba8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb, ptrdiff_t rgb_stride, const int32_t* labels,
+                          ptrdiff_t labels_stride, uint8_t* rgba, ptrdiff_t rgba_stride, int W, int H, int nlabels)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!rgb || !labels || !rgba || W <= 0 || H <= 0 || nlabels < 0 || (labels_stride & 3)) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    cudaStream_t s = pick(ctx, stream);
+    size_t sb = ((size_t)nlabels + 1) * 4 * sizeof(unsigned long long);
+    unsigned long long* sums = (unsigned long long*)ofxcv_ws(ctx, WS_MISC1, sb);
+    if (!sums) return OFXCV_ERR_MEMORY;
+    OFXCV_CUDA(ctx, cudaMemsetAsync(sums, 0, sb, s));
+    dim3 grid(ofxcv_div_up(W, 256), H);
+    cv_label_sums<<<grid, 256, 0, s>>>(rgb, rgb_stride, labels, labels_stride / 4, W, H, nlabels, sums);
+    OFXCV_LAUNCH_CHECK(ctx);
+    cv_label_paint<<<grid, 256, 0, s>>>(labels, labels_stride / 4, rgba, rgba_stride, W, H, nlabels, sums);
+    OFXCV_LAUNCH_CHECK(ctx);
+    return OFXCV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+"""Bit-exact parity of the CUDA watershed with the CPU oracle (np.array_equal on the int32 label map)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("h,w,n,seed", [(120, 160, 9, 5), (480, 640, 64, 7), (33, 47, 3, 1)])
+def test_watershed_vs_oracle(ctx, oracle, synth, h, w, n, seed):
+    img = synth.texture(h, w, seed + 10)
+    mk = synth.seed_markers(h, w, n, seed)
+    got = ctx.watershed(img, mk)
+    ref, pops = oracle.watershed(img, mk)
+    assert np.array_equal(got, ref)
+    assert ctx.watershed_stats()["pops"] == pops
+
+
+def test_watershed_white_noise_and_negatives(ctx, oracle):
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (90, 121, 3), dtype=np.uint8)
+    mk = np.zeros((90, 121), np.int32)
+    mk[10:14, 10:14] = 1
+    mk[60:64, 100:104] = 2
+    mk[40, 50] = 3
+    mk[5, 5] = -1      # stale ridge from an earlier run: must be treated as unlabelled
+    mk[0, 30] = 7      # label on the border ring: overwritten by -1
+    got = ctx.watershed(img, mk)
+    ref, _ = oracle.watershed(img, mk)
+    assert np.array_equal(got, ref)
+
+
+def test_watershed_no_seeds(ctx, oracle):
+    img = np.zeros((20, 30, 3), np.uint8)
+    mk = np.zeros((20, 30), np.int32)
+    got = ctx.watershed(img, mk)
+    ref, _ = oracle.watershed(img, mk)
+    assert np.array_equal(got, ref)
