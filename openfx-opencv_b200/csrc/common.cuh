@@ -102,6 +102,8 @@ enum {
     WS_INP_F,
     WS_INP_G,
     WS_INP_H,
+    WS_FB_SINT,  // per-band interior difference sums of the running column sum
+    WS_FB_TOT,   // per-band totals
     WS_COUNT
 };
 static_assert(WS_COUNT <= 32, "workspace slots");
