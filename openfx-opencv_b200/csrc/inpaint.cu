@@ -1,8 +1,628 @@
-// placeholder translation unit: replaced by the FMM inpaint implementation
+// FMM inpainting (Telea and Navier-Stokes) for sm_100a — the body behind the inpaint plugin's render action
+// (/root/reference/opencv2fx/inpaint/inpaint.cpp:311-318: cvInpaint(image0, mask, image1, radius, TELEA)).
+// Algorithm per SURVEY.md Appendix A.2 (OpenCV photo/inpaint.cpp as pinned by cv2 4.13); the result is bit-exact
+// with the CPU path by construction.  THIS FILE IS COMPILED WITH -fmad=false.
+//
+// The CPU algorithm is one sequential priority process.  It is split here into two exactly-equivalent stages:
+//
+//  Stage A (mask only): the fast-marching ORDER and the T values.  Entries leave the heap in (T, push-counter)
+//    order and a pixel reached by a pop at T=tau gets T' >= tau + 0.7071, so every heap entry with
+//    T in [tau_min, tau_min+0.7) can be popped as ONE parallel batch: the pixels reached by the batch get their
+//    pusher (smallest (T,counter) selected neighbour), a fill key (pusher key, neighbour slot), and -- after a
+//    radix sort of the keys -- the same push counters the CPU would hand out.  T of a reached pixel depends only
+//    on 4-neighbours reached earlier; inside a batch that is a short dependency chain resolved by relaxation
+//    rounds.  Telea runs this twice (outside band, negated; then the hole), Navier-Stokes once.
+//
+//  Stage B (colours): every hole pixel, in fill order, is a weighted sum over its radius-disc of pixels that were
+//    known or filled before it.  One WARP per pixel: tickets are handed out in fill order, a warp spins until the
+//    earlier-filled hole pixels inside its (2r+3)^2 box are done (dataflow, only ever waits on lower tickets),
+//    the lanes evaluate the taps' weights in parallel, and the f32 accumulators are then summed in the CPU's
+//    row-major tap order (one lane per accumulator) so that every rounding matches.
+#include <math.h>
+
+#include <cub/cub.cuh>
+
 #include "common.cuh"
-extern "C" {
-int ofxcv_inpaint_u8(ofxcv_ctx*, ofxcv_stream, const uint8_t*, ptrdiff_t, int, const uint8_t*, ptrdiff_t, uint8_t*, ptrdiff_t, int, int, double, int) { return OFXCV_ERR_UNSUPPORTED; }
-int ofxcv_inpaint_u8_host(ofxcv_ctx*, const uint8_t*, ptrdiff_t, int, const uint8_t*, ptrdiff_t, uint8_t*, ptrdiff_t, int, int, double, int) { return OFXCV_ERR_UNSUPPORTED; }
-size_t ofxcv_inpaint_workspace_bytes(int, int, int) { return 0; }
-int ofxcv_inpaint_last_stats(const ofxcv_ctx*, int64_t*) { return OFXCV_ERR_UNSUPPORTED; }
+
+namespace {
+
+enum : uint8_t { ST_OUT = 0, ST_INSIDE = 1, ST_HEAP = 2, ST_POPPED = 3, ST_SELECTED = 4, ST_NEW = 5 };
+constexpr float T_FAR = 1.0e6f;
+constexpr uint32_t CNT_NONE = 0xffffffffu;
+
+struct IpGeom {
+    int W, H, er, ec;  // image size, padded map size (H+2, W+2)
+    int np;            // er*ec
+};
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ip_init(const uint8_t* __restrict__ mask, ptrdiff_t mstride, uint8_t* __restrict__ hole,
+                                               float* __restrict__ t, uint32_t* __restrict__ cnt, uint16_t* __restrict__ rnd,
+                                               uint8_t* __restrict__ done, unsigned* __restrict__ counters, IpGeom g)
+{
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= g.np) return;
+    int i = id / g.ec, j = id - i * g.ec;
+    uint8_t h = 0;
+    if (i >= 1 && i <= g.H && j >= 1 && j <= g.W) h = mask[(size_t)(i - 1) * mstride + (j - 1)] != 0;
+    hole[id] = h;
+    t[id] = T_FAR;
+    cnt[id] = CNT_NONE;
+    rnd[id] = 0;
+    done[id] = 0;
+    if (h) atomicAdd(&counters[0], 1u);  // number of hole pixels
 }
+
+// band = known interior pixels with a hole 4-neighbour; heap entries with T = 0 pushed in row-major order
+// (counter = row-major id).  region: 0 -> FMM over the hole (st INSIDE on holes), 1 -> FMM over `outreg`.
+__global__ void __launch_bounds__(256) ip_setup_pass(const uint8_t* __restrict__ hole, const uint8_t* __restrict__ outreg,
+                                                     uint8_t* __restrict__ st, float* __restrict__ t, uint32_t* __restrict__ cnt,
+                                                     uint16_t* __restrict__ rnd, int outer, IpGeom g)
+{
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= g.np) return;
+    int i = id / g.ec, j = id - i * g.ec;
+    uint8_t s = ST_OUT;
+    bool interior = i >= 1 && i <= g.H && j >= 1 && j <= g.W;
+    if (interior) {
+        bool h = hole[id];
+        bool band = !h && (hole[id - g.ec] || hole[id + g.ec] || hole[id - 1] || hole[id + 1]);
+        if (band) {
+            s = ST_HEAP;
+            t[id] = 0.f;
+            cnt[id] = (uint32_t)id;
+        } else if (outer ? (outreg[id] != 0) : h) {
+            s = ST_INSIDE;
+        }
+    }
+    st[id] = s;
+    rnd[id] = 0;
+}
+
+// (2r+1)^2 rect dilation of the hole, separable; out-region = dilated & !hole & !band, border ring cleared
+__global__ void __launch_bounds__(256) ip_dilate_rows(const uint8_t* __restrict__ hole, uint8_t* __restrict__ tmp, int range, IpGeom g)
+{
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= g.np) return;
+    int i = id / g.ec, j = id - i * g.ec;
+    uint8_t v = 0;
+    for (int l = max(j - range, 0); l <= min(j + range, g.ec - 1); l++) v |= hole[i * g.ec + l];
+    tmp[id] = v;
+}
+__global__ void __launch_bounds__(256) ip_dilate_cols(const uint8_t* __restrict__ hole, const uint8_t* __restrict__ tmp,
+                                                      uint8_t* __restrict__ outreg, int range, IpGeom g)
+{
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= g.np) return;
+    int i = id / g.ec, j = id - i * g.ec;
+    uint8_t r = 0;
+    if (i >= 1 && i <= g.H && j >= 1 && j <= g.W && !hole[id]) {
+        uint8_t v = 0;
+        for (int k = max(i - range, 0); k <= min(i + range, g.er - 1); k++) v |= tmp[k * g.ec + j];
+        bool band = hole[id - g.ec] || hole[id + g.ec] || hole[id - 1] || hole[id + 1];
+        r = v && !band;
+    }
+    outreg[id] = r;
+}
+
+// ---- one batch of the marching ---------------------------------------------------------------------------
+// pass A: retire last batch (SELECTED -> POPPED, NEW -> HEAP) and find tau = min T over the heap
+__global__ void __launch_bounds__(256) ip_pass_a(uint8_t* __restrict__ st, const float* __restrict__ t, unsigned* __restrict__ tau_bits, IpGeom g)
+{
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned local = 0xffffffffu;
+    if (id < g.np) {
+        uint8_t s = st[id];
+        if (s == ST_SELECTED) st[id] = ST_POPPED;
+        else if (s == ST_NEW) { st[id] = ST_HEAP; s = ST_HEAP; }
+        if (s == ST_HEAP) local = __float_as_uint(t[id]);  // T >= 0: the bit pattern orders like the value
+    }
+    local = __reduce_min_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local != 0xffffffffu) atomicMin(tau_bits, local);
+}
+
+// pass B: select the window [tau, tau+0.7)
+__global__ void __launch_bounds__(256) ip_pass_b(uint8_t* __restrict__ st, const float* __restrict__ t, const unsigned* __restrict__ tau_bits, IpGeom g)
+{
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= g.np) return;
+    if (st[id] == ST_HEAP) {
+        float lim = __uint_as_float(*tau_bits) + 0.7f;
+        if (t[id] < lim) st[id] = ST_SELECTED;
+    }
+}
+
+// pass C: every INSIDE pixel next to a selected entry is reached in this batch; pusher = smallest (T, counter),
+// slot = position of the pixel in the pusher's neighbour order (up, left, down, right of the PUSHER)
+__global__ void __launch_bounds__(256) ip_pass_c(uint8_t* __restrict__ st, const float* __restrict__ t, const uint32_t* __restrict__ cnt,
+                                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ ids,
+                                                 unsigned* __restrict__ n_new, IpGeom g)
+{
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= g.np) return;
+    if (st[id] != ST_INSIDE) return;
+    // neighbour p of q        q = p + dir[slot]
+    //  p above  (id-ec)       slot 2 (down)
+    //  p left   (id-1)        slot 3 (right)
+    //  p below  (id+ec)       slot 0 (up)
+    //  p right  (id+1)        slot 1 (left)
+    const int nb[4] = {id - g.ec, id - 1, id + g.ec, id + 1};
+    const unsigned slot[4] = {2u, 3u, 0u, 1u};
+    unsigned long long best = ~0ull;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int p = nb[q];
+        if (st[p] == ST_SELECTED) {
+            unsigned long long k = ((unsigned long long)__float_as_uint(t[p]) << 32) | ((unsigned long long)cnt[p] << 2) | slot[q];
+            best = k < best ? k : best;
+        }
+    }
+    if (best == ~0ull) return;
+    unsigned pos = atomicAdd(n_new, 1u);
+    keys[pos] = best;
+    ids[pos] = (uint32_t)id;
+}
+
+// after the sort: hand out push counters in fill order; the hole pass also records the fill order itself
+__global__ void __launch_bounds__(256) ip_assign(const uint32_t* __restrict__ ids_sorted, unsigned n, uint32_t base,
+                                                 uint8_t* __restrict__ st, uint32_t* __restrict__ cnt, uint32_t* __restrict__ order,
+                                                 uint32_t order_base)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t id = ids_sorted[i];
+    cnt[id] = base + i;
+    st[id] = ST_NEW;
+    if (order) order[order_base + i] = id;
+}
+
+__device__ __forceinline__ float fmm_solve(bool k1, bool k2, float t1, float t2)
+{
+    double sol, a11 = t1, a22 = t2, m12 = a11 < a22 ? a11 : a22;
+    if (k1) {
+        if (k2) {
+            if (fabs(a11 - a22) >= 1.0) sol = 1 + m12;
+            else sol = (a11 + a22 + sqrt((double)(2 - (a11 - a22) * (a11 - a22)))) * 0.5;
+        } else sol = 1 + a11;
+    } else if (k2) sol = 1 + a22;
+    else sol = 1 + m12;
+    return (float)sol;
+}
+
+// relaxation round `round` (>=1): a pixel reached in this batch gets its T once every 4-neighbour reached EARLIER
+// in the same batch has its T (rnd != 0 and < round: values written in this very round are ignored -> race-free)
+__global__ void __launch_bounds__(256) ip_round(const uint32_t* __restrict__ ids_sorted, unsigned n, const uint8_t* __restrict__ st,
+                                                float* __restrict__ t, const uint32_t* __restrict__ cnt, uint16_t* __restrict__ rnd,
+                                                unsigned round, unsigned* __restrict__ pending, IpGeom g)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t id = ids_sorted[i];
+    if (rnd[id] != 0) return;
+    const uint32_t mycnt = cnt[id];
+    const int nb[4] = {(int)id - g.ec, (int)id + g.ec, (int)id - 1, (int)id + 1};  // up, down, left, right
+    bool known[4];
+    float tv[4];
+    bool ready = true;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int p = nb[q];
+        uint8_t s = st[p];
+        bool k;
+        if (s == ST_INSIDE) k = false;
+        else if (s == ST_NEW) {
+            k = cnt[p] < mycnt;
+            if (k) {
+                unsigned r = rnd[p];
+                if (r == 0 || r >= round) ready = false;
+            }
+        } else k = true;
+        known[q] = k;
+        tv[q] = t[p];
+    }
+    if (!ready) {
+        atomicAdd(pending, 1u);
+        return;
+    }
+    // min4(solve(i-1,j,i,j-1), solve(i+1,j,i,j-1), solve(i-1,j,i,j+1), solve(i+1,j,i,j+1))
+    float a = fmm_solve(known[0], known[2], tv[0], tv[2]);
+    float b = fmm_solve(known[1], known[2], tv[1], tv[2]);
+    float c = fmm_solve(known[0], known[3], tv[0], tv[3]);
+    float d = fmm_solve(known[1], known[3], tv[1], tv[3]);
+    a = a < b ? a : b;
+    c = c < d ? c : d;
+    t[id] = a < c ? a : c;
+    rnd[id] = (uint16_t)round;
+}
+
+__global__ void __launch_bounds__(256) ip_negate(const uint8_t* __restrict__ st, const uint8_t* __restrict__ outreg, float* __restrict__ t, IpGeom g)
+{
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= g.np) return;
+    if (outreg[id] && st[id] != ST_INSIDE && st[id] != ST_OUT) t[id] = -t[id];
+}
+
+__global__ void __launch_bounds__(256) ip_copy(const uint8_t* __restrict__ src, ptrdiff_t sstride, uint8_t* __restrict__ dst, ptrdiff_t dstride,
+                                               int rowbytes, int H)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= rowbytes) return;
+    dst[(size_t)y * dstride + x] = src[(size_t)y * sstride + x];
+}
+
+// ---- Stage B: colour fill, one warp per hole pixel, dataflow in fill order -------------------------------
+constexpr int IP_WARPS = 8;
+constexpr int IP_MAXACC = 12;  // Telea, 3 channels: (Ia, Jx, Jy, s) x 3
+
+__device__ __forceinline__ int ld_u8_cg(const uint8_t* p) { return (int)__ldcg(p); }
+
+template <int METHOD, int CN>
+__global__ void __launch_bounds__(IP_WARPS * 32)
+ip_fill(const uint32_t* __restrict__ order, unsigned nfill, uint32_t cnt_base, const uint8_t* __restrict__ hole,
+        const uint32_t* __restrict__ cnt, const float* __restrict__ t, uint8_t* out, ptrdiff_t ostride, uint8_t* done,
+        unsigned* __restrict__ ticket, int range, IpGeom g)
+{
+    constexpr int NACC = METHOD == OFXCV_INPAINT_TELEA ? 4 * CN : 2 * CN;
+    __shared__ float s_term[IP_WARPS][32][IP_MAXACC + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ec = g.ec, er = g.er;
+    const int side = 2 * range + 1, ntaps = side * side;
+    const int bside = 2 * range + 3, nbox = bside * bside;
+    volatile uint8_t* vdone = done;
+
+    for (;;) {
+        unsigned tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1u);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk >= nfill) break;
+        const int id = (int)order[tk];
+        const uint32_t mycnt = cnt_base + tk;
+        const int i = id / ec, j = id - i * ec;
+
+        // 1. wait for every earlier-filled hole pixel of the (2r+3)^2 box
+        for (int b = lane; b < nbox; b += 32) {
+            int k = i - range - 1 + b / bside, l = j - range - 1 + b % bside;
+            if (k < 1 || l < 1 || k > g.H || l > g.W) continue;
+            int n = k * ec + l;
+            if (hole[n] && cnt[n] < mycnt) {
+                while (vdone[n] == 0) { }
+            }
+        }
+        __syncwarp();
+        __threadfence();
+
+        // a pixel is "not INSIDE" at this pixel's fill time iff it is not a hole or was filled earlier
+        auto known = [&](int n) -> bool { return !hole[n] || cnt[n] < mycnt; };
+
+        float gTx = 0.f, gTy = 0.f, ti = 0.f;
+        if (METHOD == OFXCV_INPAINT_TELEA) {
+            ti = t[id];
+            if (known(id + 1)) {
+                if (known(id - 1)) gTx = (float)(t[id + 1] - t[id - 1]) * 0.5f;
+                else gTx = (float)(t[id + 1] - ti);
+            } else {
+                if (known(id - 1)) gTx = (float)(ti - t[id - 1]);
+                else gTx = 0;
+            }
+            if (known(id + ec)) {
+                if (known(id - ec)) gTy = (float)(t[id + ec] - t[id - ec]) * 0.5f;
+                else gTy = (float)(t[id + ec] - ti);
+            } else {
+                if (known(id - ec)) gTy = (float)(ti - t[id - ec]);
+                else gTy = 0;
+            }
+        }
+
+        float acc = 0.f;  // lane a < NACC owns accumulator a
+        if (METHOD == OFXCV_INPAINT_TELEA) { if ((lane & 3) == 3) acc = 1.0e-20f; }
+        else { if ((lane & 1) == 1) acc = 1.0e-20f; }
+
+        for (int base = 0; base < ntaps; base += 32) {
+            const int tp = base + lane;
+            bool valid = false;
+            float term[IP_MAXACC];
+#pragma unroll
+            for (int a = 0; a < IP_MAXACC; a++) term[a] = 0.f;
+            if (tp < ntaps) {
+                const int k = i - range + tp / side, l = j - range + tp % side;
+                if (k > 0 && l > 0 && k < er - 1 && l < ec - 1) {
+                    const int n = k * ec + l;
+                    if (known(n) && (l - j) * (l - j) + (k - i) * (k - i) <= range * range) {
+                        valid = true;
+                        const int km = k - 1 + (k == 1), kp = k - 1 - (k == er - 2);
+                        const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ec - 2);
+                        const bool fr = known(n + 1), fl = known(n - 1), fd = known(n + ec), fu = known(n - ec);
+#define OUTP(r, c, ch) ld_u8_cg(out + (size_t)(r) * ostride + (size_t)(c) * CN + (ch))
+                        if (METHOD == OFXCV_INPAINT_TELEA) {
+                            float ry = (float)(i - k), rx = (float)(j - l);
+                            float vl = rx * rx + ry * ry;
+                            float dst = (float)(1. / (vl * sqrt((double)vl)));
+                            float lev = (float)(1. / (1 + fabs(t[n] - ti)));
+                            float dir = rx * gTx + ry * gTy;
+                            if (fabs(dir) <= 0.01) dir = 0.000001f;
+                            float w = (float)fabs(dst * lev * dir);
+#pragma unroll
+                            for (int c = 0; c < CN; c++) {
+                                float gIx, gIy;
+                                if (fr) {
+                                    if (fl) gIx = (float)(OUTP(km, lp + 1, c) - OUTP(km, lm - 1, c)) * 2.0f;
+                                    else gIx = (float)(OUTP(km, lp + 1, c) - OUTP(km, lm, c));
+                                } else {
+                                    if (fl) gIx = (float)(OUTP(km, lp, c) - OUTP(km, lm - 1, c));
+                                    else gIx = 0;
+                                }
+                                if (fd) {
+                                    if (fu) gIy = (float)(OUTP(kp + 1, lm, c) - OUTP(km - 1, lm, c)) * 2.0f;
+                                    else gIy = (float)(OUTP(kp + 1, lm, c) - OUTP(km, lm, c));
+                                } else {
+                                    if (fu) gIy = (float)(OUTP(kp, lm, c) - OUTP(km - 1, lm, c));
+                                    else gIy = 0;
+                                }
+                                term[c * 4 + 0] = w * (float)OUTP(k - 1, l - 1, c);
+                                term[c * 4 + 1] = -(w * (gIx * rx));
+                                term[c * 4 + 2] = -(w * (gIy * ry));
+                                term[c * 4 + 3] = w;
+                            }
+                        } else {
+                            float ry = (float)(k - i), rx = (float)(l - j);
+                            float vl = rx * rx + ry * ry;
+                            float dst = 1 / (vl * vl + 1);
+#pragma unroll
+                            for (int c = 0; c < CN; c++) {
+                                float gIx, gIy;
+                                if (fd) {
+                                    if (fu) gIx = (float)(abs(OUTP(kp + 1, lm, c) - OUTP(kp, lm, c)) + abs(OUTP(kp, lm, c) - OUTP(km - 1, lm, c)));
+                                    else gIx = (float)(abs(OUTP(kp + 1, lm, c) - OUTP(kp, lm, c))) * 2.0f;
+                                } else {
+                                    if (fu) gIx = (float)(abs(OUTP(kp, lm, c) - OUTP(km - 1, lm, c))) * 2.0f;
+                                    else gIx = 0;
+                                }
+                                if (fr) {
+                                    if (fl) gIy = (float)(abs(OUTP(km, lp + 1, c) - OUTP(km, lm, c)) + abs(OUTP(km, lm, c) - OUTP(km, lm - 1, c)));
+                                    else gIy = (float)(abs(OUTP(km, lp + 1, c) - OUTP(km, lm, c))) * 2.0f;
+                                } else {
+                                    if (fl) gIy = (float)(abs(OUTP(km, lm, c) - OUTP(km, lm - 1, c))) * 2.0f;
+                                    else gIy = 0;
+                                }
+                                gIx = -gIx;
+                                float dir = rx * gIx + ry * gIy;
+                                if (fabs(dir) <= 0.01) dir = 0.000001f;
+                                else dir = fabsf((rx * gIx + ry * gIy) / sqrtf(vl * (gIx * gIx + gIy * gIy)));
+                                float w = dst * dir;
+                                term[c * 2 + 0] = w * (float)OUTP(k - 1, l - 1, c);
+                                term[c * 2 + 1] = w;
+                            }
+                        }
+#undef OUTP
+                    }
+                }
+            }
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+#pragma unroll
+                for (int a = 0; a < NACC; a++) s_term[wid][lane][a] = term[a];
+            }
+            __syncwarp();
+            if (lane < NACC) {
+                unsigned m = vmask;
+                while (m) {
+                    int tl = __ffs(m) - 1;
+                    m &= m - 1;
+                    acc = acc + s_term[wid][tl][lane];
+                }
+            }
+            __syncwarp();
+        }
+
+        // 3. finish: lane c gathers its channel's accumulators
+        uint8_t result = 0;
+        if (METHOD == OFXCV_INPAINT_TELEA) {
+            int c = lane < CN ? lane : 0;
+            float Ia = __shfl_sync(0xffffffffu, acc, c * 4 + 0);
+            float Jx = __shfl_sync(0xffffffffu, acc, c * 4 + 1);
+            float Jy = __shfl_sync(0xffffffffu, acc, c * 4 + 2);
+            float s = __shfl_sync(0xffffffffu, acc, c * 4 + 3);
+            float sat = Ia / s + (Jx + Jy) / (sqrtf(Jx * Jx + Jy * Jy) + 1.0e-20f) + 0.5f;
+            int iv = __double2int_rn((double)sat);
+            result = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+        } else {
+            int c = lane < CN ? lane : 0;
+            float Ia = __shfl_sync(0xffffffffu, acc, c * 2 + 0);
+            float s = __shfl_sync(0xffffffffu, acc, c * 2 + 1);
+            int iv = __double2int_rn((double)Ia / s);
+            result = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+        }
+        if (lane < CN) {
+            volatile uint8_t* o = out + (size_t)(i - 1) * ostride + (size_t)(j - 1) * CN + lane;
+            *o = result;
+        }
+        __syncwarp();
+        __threadfence();
+        if (lane == 0) vdone[id] = 1;
+    }
+}
+
+struct IpCounters {
+    unsigned nholes, tau_bits, n_new, pending, ticket, pad[3];
+};
+
+}  // namespace
+
+extern "C" {
+
+size_t ofxcv_inpaint_workspace_bytes(int W, int H, int channels)
+{
+    (void)channels;
+    size_t np = (size_t)(W + 2) * (H + 2);
+    // hole, outreg, tmp, st, done (1 B), rnd (2 B), t, cnt, order, ids x2 (4 B), keys x2 (8 B), + sort temp
+    return np * (5 + 2 + 4 * 5 + 16) + np * 8 + 4096;
+}
+
+int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, ptrdiff_t img_stride, int channels,
+                     const uint8_t* mask, ptrdiff_t mask_stride, uint8_t* out, ptrdiff_t out_stride, int W, int H, double radius,
+                     int method)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!img || !mask || !out || W < 2 || H < 2 || (channels != 1 && channels != 3) || img_stride < (ptrdiff_t)W * channels ||
+        out_stride < (ptrdiff_t)W * channels || mask_stride < W || (method != OFXCV_INPAINT_NS && method != OFXCV_INPAINT_TELEA))
+        return OFXCV_ERR_BAD_ARG;
+    if ((size_t)(W + 2) * (H + 2) >= ((size_t)1 << 28)) return OFXCV_ERR_UNSUPPORTED;
+    ofxcv_device_guard guard(ctx->device);
+    cudaStream_t s = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+    int range = (int)nearbyint(radius);
+    range = range < 1 ? 1 : range > 100 ? 100 : range;
+
+    IpGeom g;
+    g.W = W; g.H = H; g.er = H + 2; g.ec = W + 2; g.np = g.er * g.ec;
+    const size_t np = (size_t)g.np;
+    uint8_t* bytes = (uint8_t*)ofxcv_ws(ctx, WS_INP_A, np * 5);
+    uint16_t* rnd = (uint16_t*)ofxcv_ws(ctx, WS_INP_B, np * 2);
+    float* t = (float*)ofxcv_ws(ctx, WS_INP_C, np * 4);
+    uint32_t* u32s = (uint32_t*)ofxcv_ws(ctx, WS_INP_D, np * 4 * 4);
+    unsigned long long* keys = (unsigned long long*)ofxcv_ws(ctx, WS_INP_E, np * 8 * 2);
+    IpCounters* ctr = (IpCounters*)ofxcv_ws(ctx, WS_INP_F, sizeof(IpCounters));
+    IpCounters* hctr = (IpCounters*)ofxcv_pin(ctx, 2, sizeof(IpCounters));
+    if (!bytes || !rnd || !t || !u32s || !keys || !ctr || !hctr) return OFXCV_ERR_MEMORY;
+    uint8_t *hole = bytes, *outreg = bytes + np, *tmp = bytes + 2 * np, *st = bytes + 3 * np, *done = bytes + 4 * np;
+    uint32_t *cnt = u32s, *order = u32s + np, *ids = u32s + 2 * np, *ids_sorted = u32s + 3 * np;
+    unsigned long long* keys_sorted = keys + np;
+    size_t sort_tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, keys, keys_sorted, ids, ids_sorted, g.np, 0, 64, s);
+    void* sort_tmp = ofxcv_ws(ctx, WS_INP_G, sort_tmp_bytes);
+    if (!sort_tmp) return OFXCV_ERR_MEMORY;
+
+    const int nblk = ofxcv_div_up(g.np, 256);
+    uint64_t launches0 = ctx->launches;
+    int64_t batches = 0, rounds_total = 0;
+    OFXCV_CUDA(ctx, cudaMemsetAsync(ctr, 0, sizeof(IpCounters), s));
+    ip_init<<<nblk, 256, 0, s>>>(mask, mask_stride, hole, t, cnt, rnd, done, &ctr->nholes, g);
+    OFXCV_LAUNCH_CHECK(ctx);
+    if (out != img) {
+        ip_copy<<<dim3(ofxcv_div_up(W * channels, 256), H), 256, 0, s>>>(img, img_stride, out, out_stride, W * channels, H);
+        OFXCV_LAUNCH_CHECK(ctx);
+    }
+    OFXCV_CUDA(ctx, cudaMemcpyAsync(hctr, ctr, sizeof(IpCounters), cudaMemcpyDeviceToHost, s));
+    OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+    const unsigned nholes = hctr->nholes;
+    ctx->inpaint_stats[0] = nholes;
+    ctx->inpaint_stats[1] = ctx->inpaint_stats[2] = ctx->inpaint_stats[3] = 0;
+    if (nholes == 0) return OFXCV_OK;
+
+    if (method == OFXCV_INPAINT_TELEA) {
+        ip_dilate_rows<<<nblk, 256, 0, s>>>(hole, tmp, range, g);
+        OFXCV_LAUNCH_CHECK(ctx);
+        ip_dilate_cols<<<nblk, 256, 0, s>>>(hole, tmp, outreg, range, g);
+        OFXCV_LAUNCH_CHECK(ctx);
+    }
+    uint32_t nfilled = 0;
+    for (int pass = (method == OFXCV_INPAINT_TELEA ? 1 : 0); pass >= 0; pass--) {
+        const int outer = pass;  // Telea: pass 1 = outside band (negated afterwards), pass 0 = the hole itself
+        ip_setup_pass<<<nblk, 256, 0, s>>>(hole, outreg, st, t, cnt, rnd, outer, g);
+        OFXCV_LAUNCH_CHECK(ctx);
+        uint32_t next_cnt = (uint32_t)g.np;  // reached pixels get counters above every band counter
+        for (;;) {
+            OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->tau_bits, 0xff, sizeof(unsigned), s));
+            OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->n_new, 0, sizeof(unsigned), s));
+            ip_pass_a<<<nblk, 256, 0, s>>>(st, t, &ctr->tau_bits, g);
+            OFXCV_LAUNCH_CHECK(ctx);
+            ip_pass_b<<<nblk, 256, 0, s>>>(st, t, &ctr->tau_bits, g);
+            OFXCV_LAUNCH_CHECK(ctx);
+            ip_pass_c<<<nblk, 256, 0, s>>>(st, t, cnt, keys, ids, &ctr->n_new, g);
+            OFXCV_LAUNCH_CHECK(ctx);
+            OFXCV_CUDA(ctx, cudaMemcpyAsync(hctr, ctr, sizeof(IpCounters), cudaMemcpyDeviceToHost, s));
+            OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+            if (hctr->tau_bits == 0xffffffffu) break;  // heap empty
+            batches++;
+            const unsigned n_new = hctr->n_new;
+            if (n_new == 0) continue;
+            OFXCV_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp, sort_tmp_bytes, keys, keys_sorted, ids, ids_sorted, (int)n_new, 0, 64, s));
+            ctx->launches += 4;
+            const int nb2 = ofxcv_div_up((int)n_new, 256);
+            ip_assign<<<nb2, 256, 0, s>>>(ids_sorted, n_new, next_cnt, st, cnt, outer ? nullptr : order, nfilled);
+            OFXCV_LAUNCH_CHECK(ctx);
+            next_cnt += n_new;
+            if (!outer) nfilled += n_new;
+            // relaxation rounds until every reached pixel has its T
+            unsigned round = 1;
+            for (;;) {
+                const int burst = round == 1 ? 4 : 16;
+                for (int b = 0; b < burst; b++, round++) {
+                    if (round >= 65535) return OFXCV_ERR_UNSUPPORTED;
+                    OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->pending, 0, sizeof(unsigned), s));
+                    ip_round<<<nb2, 256, 0, s>>>(ids_sorted, n_new, st, t, cnt, rnd, round, &ctr->pending, g);
+                    OFXCV_LAUNCH_CHECK(ctx);
+                }
+                OFXCV_CUDA(ctx, cudaMemcpyAsync(hctr, ctr, sizeof(IpCounters), cudaMemcpyDeviceToHost, s));
+                OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+                if (hctr->pending == 0) break;
+            }
+            rounds_total += round - 1;
+        }
+        if (outer) {
+            ip_negate<<<nblk, 256, 0, s>>>(st, outreg, t, g);
+            OFXCV_LAUNCH_CHECK(ctx);
+        }
+    }
+
+    // Stage B
+    if (nfilled > 0) {
+        OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->ticket, 0, sizeof(unsigned), s));
+        int blocks = ctx->num_sms * 8;
+        int need = ofxcv_div_up((int)nfilled, IP_WARPS);
+        if (blocks > need) blocks = need;
+        ofxcv_time_begin(ctx, 1, s);
+#define IP_FILL(M, C) ip_fill<M, C><<<blocks, IP_WARPS * 32, 0, s>>>(order, nfilled, (uint32_t)g.np, hole, cnt, t, out, out_stride, done, &ctr->ticket, range, g)
+        if (method == OFXCV_INPAINT_TELEA) {
+            if (channels == 3) IP_FILL(OFXCV_INPAINT_TELEA, 3);
+            else IP_FILL(OFXCV_INPAINT_TELEA, 1);
+        } else {
+            if (channels == 3) IP_FILL(OFXCV_INPAINT_NS, 3);
+            else IP_FILL(OFXCV_INPAINT_NS, 1);
+        }
+#undef IP_FILL
+        ofxcv_time_end(ctx, 1, s);
+        OFXCV_LAUNCH_CHECK(ctx);
+    }
+    ctx->inpaint_stats[1] = batches;
+    ctx->inpaint_stats[2] = rounds_total;
+    ctx->inpaint_stats[3] = (int64_t)(ctx->launches - launches0);
+    return OFXCV_OK;
+}
+
+int ofxcv_inpaint_last_stats(const ofxcv_ctx* ctx, int64_t stats[4])
+{
+    if (!ctx || !stats) return OFXCV_ERR_BAD_ARG;
+    for (int i = 0; i < 4; i++) stats[i] = ctx->inpaint_stats[i];
+    return OFXCV_OK;
+}
+
+int ofxcv_inpaint_u8_host(ofxcv_ctx* ctx, const uint8_t* img, ptrdiff_t img_stride, int channels, const uint8_t* mask,
+                          ptrdiff_t mask_stride, uint8_t* out, ptrdiff_t out_stride, int W, int H, double radius, int method)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!img || !mask || !out || W < 2 || H < 2 || (channels != 1 && channels != 3)) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    const size_t rb = (size_t)W * channels, nimg = rb * H, nmask = (size_t)W * H;
+    uint8_t* hi = (uint8_t*)ofxcv_pin(ctx, 0, nimg + nmask);
+    uint8_t* ho = (uint8_t*)ofxcv_pin(ctx, 1, nimg);
+    uint8_t* di = (uint8_t*)ofxcv_ws(ctx, WS_STAGE_IN0, nimg);
+    uint8_t* dm = (uint8_t*)ofxcv_ws(ctx, WS_STAGE_IN1, nmask);
+    uint8_t* dout = (uint8_t*)ofxcv_ws(ctx, WS_STAGE_OUT, nimg);
+    if (!hi || !ho || !di || !dm || !dout) return OFXCV_ERR_MEMORY;
+    for (int y = 0; y < H; y++) {
+        memcpy(hi + (size_t)y * rb, img + (size_t)y * img_stride, rb);
+        memcpy(hi + nimg + (size_t)y * W, mask + (size_t)y * mask_stride, W);
+    }
+    cudaStream_t s = ctx->stream;
+    OFXCV_CUDA(ctx, cudaMemcpyAsync(di, hi, nimg, cudaMemcpyHostToDevice, s));
+    OFXCV_CUDA(ctx, cudaMemcpyAsync(dm, hi + nimg, nmask, cudaMemcpyHostToDevice, s));
+    int st = ofxcv_inpaint_u8(ctx, s, di, (ptrdiff_t)rb, channels, dm, W, dout, (ptrdiff_t)rb, W, H, radius, method);
+    if (st < 0) return st;
+    OFXCV_CUDA(ctx, cudaMemcpyAsync(ho, dout, nimg, cudaMemcpyDeviceToHost, s));
+    OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+    for (int y = 0; y < H; y++) memcpy(out + (size_t)y * out_stride, ho + (size_t)y * rb, rb);
+    return OFXCV_OK;
+}
+
+}  // extern "C"

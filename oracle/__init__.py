@@ -127,3 +127,23 @@ def inpaint(img, mask, radius, method, want_debug=False):
     lib().orc_inpaint(_p(img), C.c_int(w * cn), _p(mask), C.c_int(w), _p(out), C.c_int(w * cn), C.c_int(w), C.c_int(h), C.c_int(cn),
                       C.c_double(radius), C.c_int(method), _p(t) if want_debug else None, _p(seq) if want_debug else None)
     return (out, t, seq) if want_debug else out
+
+
+def srgb_tables():
+    to = np.empty(0x10000, np.uint16)
+    fr = np.empty(256, np.float32)
+    lib().orc_srgb_tables(_p(to), _p(fr))
+    return to, fr
+
+
+def srgb_from_byte_table():
+    return srgb_tables()[1]
+
+
+def luma_srgb_gray8(img):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape[:2]
+    nc = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty((h, w), np.uint8)
+    lib().orc_luma_srgb_gray8(_p(img), C.c_int(nc), _p(out), C.c_int(w), C.c_int(h))
+    return out

@@ -1,0 +1,76 @@
+"""Staging conversions either side of the filter bodies, against numpy restatements and the oracle LUT."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_luma_srgb_gray8(ctx, oracle):
+    rng = np.random.default_rng(0)
+    img = rng.random((37, 53, 4), dtype=np.float32) * 1.2 - 0.1   # includes <0 and >1
+    img[0, 0] = [0, 0, 0, 1]; img[0, 1] = [1, 1, 1, 1]; img[0, 2] = [np.inf, 0, 0, 1]; img[0, 3] = [np.nan, 0, 0, 1]
+    got = ctx.rgba32f_to_srgb_gray8(img)
+    ref = oracle.luma_srgb_gray8(img)
+    assert np.array_equal(got, ref)
+    got3 = ctx.rgba32f_to_srgb_gray8(np.ascontiguousarray(img[..., :3]))
+    assert np.array_equal(got3, ref)
+
+
+def test_srgb_bytes_roundtrip(ctx, oracle):
+    # every 8-bit code, converted to linear with the LUT's from-table, must come back unchanged
+    lin = oracle.srgb_from_byte_table()
+    img = np.zeros((1, 256, 4), np.float32)
+    img[0, :, 0] = img[0, :, 1] = img[0, :, 2] = lin
+    got = ctx.rgba32f_to_srgb_gray8(img)
+    # luma of (v,v,v) in double = v*(0.2126+0.7152+0.0722) may differ from v by an ulp: allow +-1 code there
+    assert np.abs(got[0].astype(int) - np.arange(256)).max() <= 1
+    one = ctx.rgba32f_to_srgb_gray8(lin.reshape(1, 256))
+    assert np.array_equal(one[0], np.arange(256, dtype=np.uint8))
+
+
+def test_flow_to_rgba(ctx):
+    rng = np.random.default_rng(1)
+    flow = rng.standard_normal((19, 23, 2)).astype(np.float32) * 5
+    dst = rng.random((19, 23, 4), dtype=np.float32)
+    got = ctx.flow_to_rgba32f(flow, dst, [0, 1, -1, 0], 0.5, 0.25)
+    ref = dst.copy()
+    ref[..., 0] = (flow[..., 0].astype(np.float64) / 0.5).astype(np.float32)
+    ref[..., 1] = (flow[..., 1].astype(np.float64) / 0.25).astype(np.float32)
+    ref[..., 3] = ref[..., 0]
+    assert np.array_equal(got, ref)
+
+
+def test_rgba8_split_mask_dilate(ctx, synth):
+    rng = np.random.default_rng(2)
+    rgba = rng.integers(0, 256, (31, 45, 4), dtype=np.uint8)
+    rgba[rng.random((31, 45)) < 0.05, :3] = 0
+    rgba[3, 4, :3] = [1, 0, 3]   # gray rounds to 0 -> counts as hole, like cvCvtColor
+    for n in (0, 1, 2):
+        rgb, mask = ctx.rgba8_to_rgb8_mask(rgba, n)
+        assert np.array_equal(rgb, rgba[..., :3])
+        ref = (synth.gray(rgba[..., :3]) == 0)
+        if n:
+            pad = np.pad(ref, n)
+            ref = np.zeros_like(ref)
+            for dy in range(2 * n + 1):
+                for dx in range(2 * n + 1):
+                    ref |= pad[dy:dy + 31, dx:dx + 45]
+        assert np.array_equal(mask, ref.astype(np.uint8) * 255)
+
+
+def test_rgb_to_rgba_and_seed_grid_and_paint(ctx, oracle, synth):
+    rgb = synth.texture(40, 50, 3)
+    rgba = ctx.rgb8_to_rgba8(rgb)
+    assert np.array_equal(rgba[..., :3], rgb) and (rgba[..., 3] == 255).all()
+    mk = ctx.seed_grid(50, 40, 4, 3, 1)
+    assert set(np.unique(mk)) == set(range(13))
+    assert all((mk == l).sum() == 9 for l in range(1, 13))
+    lab = ctx.watershed(rgb, mk)
+    ref, _ = oracle.watershed(rgb, mk)
+    assert np.array_equal(lab, ref)
+    vis = ctx.labels_to_rgba8(rgb, lab, 12)
+    for l in (1, 7, 12):
+        sel = lab == l
+        mean = np.floor(rgb[sel].astype(np.float64).mean(axis=0) + 0.5 + 1e-9)
+        assert np.abs(vis[sel][0, :3].astype(int) - mean).max() <= 1
+    assert (vis[lab == -1][:, :3] == 0).all()
