@@ -117,9 +117,12 @@ OFXCV_API int ofxcv_inpaint_u8_host(ofxcv_ctx* ctx, const uint8_t* img, ptrdiff_
                                     const uint8_t* mask, ptrdiff_t mask_stride, uint8_t* out, ptrdiff_t out_stride,
                                     int W, int H, double radius, int method);
 OFXCV_API size_t ofxcv_inpaint_workspace_bytes(int W, int H, int channels);
-/* statistics of the last inpaint call on ctx: [0]=hole pixels, [1]=dependency levels (parallel fill waves),
- * [2]=pixels marched sequentially (not covered by the closed-form first ring), [3]=fill kernel launches */
+/* statistics of the last inpaint call on ctx: [0]=hole pixels, [1]=marching batches (0.7-wide T windows popped
+ * in parallel), [2]=T relaxation rounds over all batches, [3]=kernel launches of the call */
 OFXCV_API int ofxcv_inpaint_last_stats(const ofxcv_ctx* ctx, int64_t stats[4]);
+/* test hook: after an inpaint call of size WxH on ctx, copy out the marched T map ((H+2)x(W+2) f32, padded like
+ * OpenCV's) and the fill order (HxW int32, -1 where nothing was filled).  Either pointer may be NULL. */
+OFXCV_API int ofxcv_inpaint_debug_maps(ofxcv_ctx* ctx, int W, int H, float* t_host, int32_t* order_host);
 
 /* ---- segmentation ----------------------------------------------------------------------------------- */
 /* Replaces the segment plugin's body (cvPyrSegmentation at /root/reference/opencv2fx/segment/segment.cpp:296-302)

@@ -94,6 +94,7 @@ def lib():
         "ofxcv_inpaint_u8_host": (i, [vp, vp, pd, i, vp, pd, vp, pd, i, i, d, i]),
         "ofxcv_inpaint_workspace_bytes": (sz, [i, i, i]),
         "ofxcv_inpaint_last_stats": (i, [vp, C.POINTER(C.c_int64)]),
+        "ofxcv_inpaint_debug_maps": (i, [vp, i, i, vp, vp]),
         "ofxcv_watershed_u8c3": (i, [vp, vp, vp, pd, vp, pd, i, i]),
         "ofxcv_watershed_u8c3_host": (i, [vp, vp, pd, vp, pd, i, i]),
         "ofxcv_watershed_u8c3_batch": (i, [vp, vp, vp, pd, sz, vp, pd, sz, i, i, i]),
@@ -258,7 +259,14 @@ class Context:
     def inpaint_stats(self):
         s = (C.c_int64 * 4)()
         self._check(lib().ofxcv_inpaint_last_stats(self.h, s), "ofxcv_inpaint_last_stats")
-        return dict(hole_pixels=s[0], levels=s[1], sequential_pixels=s[2], fill_launches=s[3])
+        return dict(hole_pixels=s[0], batches=s[1], rounds=s[2], launches=s[3])
+
+    def inpaint_debug_maps(self, w, h):
+        """(T map (h+2)x(w+2) float32, fill order hxw int32) of the last inpaint call — test hook."""
+        t = np.empty((h + 2, w + 2), np.float32)
+        order = np.empty((h, w), np.int32)
+        self._check(lib().ofxcv_inpaint_debug_maps(self.h, w, h, _hp(t), _hp(order)), "ofxcv_inpaint_debug_maps")
+        return t, order
 
     def watershed(self, rgb, markers):
         """rgb HxWx3 uint8, markers HxW int32 -> new label map (cv2.watershed semantics; input not modified)."""

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) ip_round(const uint32_t* __restrict__ ids
             }
         } else k = true;
         known[q] = k;
-        tv[q] = t[p];
+        tv[q] = k ? t[p] : T_FAR;  // an unreached pixel still carries T = 1e6 on the CPU at this moment
     }
     if (!ready) {
         atomicAdd(pending, 1u);
@@ -587,6 +587,29 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
     ctx->inpaint_stats[1] = batches;
     ctx->inpaint_stats[2] = rounds_total;
     ctx->inpaint_stats[3] = (int64_t)(ctx->launches - launches0);
+    return OFXCV_OK;
+}
+
+int ofxcv_inpaint_debug_maps(ofxcv_ctx* ctx, int W, int H, float* t_host, int32_t* order_host)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    const size_t np = (size_t)(W + 2) * (H + 2);
+    if (!ctx->ws[WS_INP_C].p || ctx->ws[WS_INP_C].cap < np * 4 || !ctx->ws[WS_INP_D].p) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    OFXCV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (t_host) OFXCV_CUDA(ctx, cudaMemcpy(t_host, ctx->ws[WS_INP_C].p, np * 4, cudaMemcpyDeviceToHost));
+    if (order_host) {
+        // cnt map -> fill order per image pixel (-1 where not a filled hole pixel)
+        std::vector<uint32_t> cnt(np);
+        std::vector<uint8_t> hole(np);
+        OFXCV_CUDA(ctx, cudaMemcpy(cnt.data(), ctx->ws[WS_INP_D].p, np * 4, cudaMemcpyDeviceToHost));
+        OFXCV_CUDA(ctx, cudaMemcpy(hole.data(), ctx->ws[WS_INP_A].p, np, cudaMemcpyDeviceToHost));
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                size_t id = (size_t)(y + 1) * (W + 2) + (x + 1);
+                order_host[(size_t)y * W + x] = (hole[id] && cnt[id] != 0xffffffffu) ? (int32_t)(cnt[id] - (uint32_t)np) : -1;
+            }
+    }
     return OFXCV_OK;
 }
 

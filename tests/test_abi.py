@@ -1,0 +1,74 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/ofxcv_abi.h declares; host-side
+planning helpers give the documented numbers; nothing computes without a GPU (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.lib()
+    names = pkg.declared_symbols()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), "libofxcv_b200.so does not export " + n
+    # and the python binding declares a signature for each of them
+    assert set(names) == set(L._ofxcv_sigs)
+    assert L.ofxcv_abi_version() == 1
+
+
+def test_only_abi_symbols_are_exported(pkg):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", pkg.LIB_PATH]).decode()
+    syms = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    extra = [s for s in syms if not s.startswith("ofxcv_") and s not in ("_init", "_fini")]
+    assert not extra, extra
+
+
+def test_planning_helpers(pkg):
+    p = pkg.FbParams()
+    assert pkg.farneback_scales(1920, 1080, p) == 4
+    assert pkg.farneback_scales(7680, 4320, pkg.FbParams(levels=5)) == 6
+    assert pkg.farneback_scales(100, 100, p) == 2
+    # 3.83 GB per 1080p pair, 15.33 GB per 4K pair, 61.7 GB per 8K/5-level pair
+    assert abs(pkg.farneback_algorithmic_bytes(1920, 1080, p) / 1e9 - 3.83) < 0.01
+    assert abs(pkg.farneback_algorithmic_bytes(3840, 2160, p) / 1e9 - 15.33) < 0.01
+    assert abs(pkg.farneback_algorithmic_bytes(7680, 4320, pkg.FbParams(levels=5)) / 1e9 - 61.7) < 0.1
+    L = pkg.lib()
+    d = pkg.FbParams(0, 0, 0, 0, 0, 0, 9)
+    L.ofxcv_fb_default_params(C.byref(d))
+    assert (d.pyr_scale, d.levels, d.winsize, d.iterations, d.poly_n, d.poly_sigma, d.flags) == (0.5, 3, 3, 15, 5, 1.1, 0)
+    assert L.ofxcv_status_string(0) == b"ok" and b"device" in L.ofxcv_status_string(-2)
+    assert L.ofxcv_farneback_scales(1920, 1080, C.byref(pkg.FbParams(winsize=7))) == -5
+
+
+def test_no_device_means_no_compute(pkg):
+    L = pkg.lib()
+    if L.ofxcv_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    assert L.ofxcv_create(0) is None
+    with pytest.raises(pkg.OfxcvError):
+        pkg.Context(0)
+    # every op refuses a NULL context instead of falling back to the CPU
+    assert L.ofxcv_farneback_u8_host(None, None, None, 0, 0, 0, None, 0, None) == -2
+    assert L.ofxcv_inpaint_u8_host(None, None, 0, 3, None, 0, None, 0, 0, 0, 3.0, 1) == -2
+    assert L.ofxcv_watershed_u8c3_host(None, None, 0, None, 0, 0, 0) == -2
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package, include/ or the OFX glue may reference it."""
+    bad = []
+    for base in ("openfx-opencv_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            if "build" in dp.split(os.sep):
+                continue
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".c")):
+                    continue
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"^\s*(import|from)\s+oracle\b|libofxcv_oracle|oracle/", text, re.M):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -52,6 +52,23 @@ def test_inpaint_c1_640x480(ctx, oracle, synth, method):
     assert st["hole_pixels"] == int((mask != 0).sum())
 
 
+def test_inpaint_march_order_and_T(ctx, oracle, synth):
+    """The marching stage alone: T map and fill order must equal the sequential CPU march."""
+    h, w = 60, 84
+    img = synth.texture(h, w, 2)
+    for mask in (synth.iid_mask(h, w, 3, 0.3), synth.blob_mask(h, w, 5, nblobs=6, rmax=12)):
+        for method in (TELEA, NS):
+            got = ctx.inpaint(img, mask, 3, method)
+            t, order = ctx.inpaint_debug_maps(w, h)
+            ref, t_ref, seq_ref = oracle.inpaint(img, mask, 3, method, want_debug=True)
+            assert np.array_equal(order, seq_ref)
+            hole = np.pad(mask != 0, 1)
+            assert np.array_equal(t[hole], t_ref[hole])
+            if method == TELEA:
+                assert np.array_equal(t, t_ref)
+            assert np.array_equal(got, ref)
+
+
 def test_inpaint_large_blob(ctx, oracle, synth):
     img = synth.texture(200, 260, 7)
     mask = synth.blob_mask(200, 260, 9, nblobs=4, rmax=30)
