@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — 4K frames/s of the Farneback optical-flow hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU; torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's OpenCV CPU path, rank 0 only
+
+A "step" = one pass of the hot path over one batch of synthetic 3840x2160 frame pairs per GPU (default 8 pairs,
+default plugin parameters: levels 3, winsize 3, 15 iterations, polyN 5, sigma 1.1).  Frames of the sequence are
+sharded one block per GPU with no data-path collective (weak scaling: per-GPU work is fixed).
+  value  = flow fields (frame pairs) per second, whole job, frames already resident in HBM, CUDA-event timed,
+           max over ranks, barrier + synchronize on both sides;
+  e2e    = the same metric through the host-buffer C-ABI call (ofxcv_farneback_u8_host) with page-locked host
+           frames: H2D of both frames and D2H of the flow field inside the timed region, every step;
+  roofline = the Farneback iteration kernels (fb_band_totals + fb_band): algorithmic bytes (88 B per scale-pixel
+           per iteration, 28 for the last one: SURVEY.md 8d) / their CUDA-event time inside the timed region,
+           against the measured HBM copy peak in MEASURED_PEAKS.json (fallback 6650 GB/s);
+  cpu_baseline = the reference arm run once on this box's host cores on a bounded sample (rank 0, N=1 only).
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W4K, H4K = 3840, 2160
+METRIC = "4K frames/sec, Farneback optical flow (VectorGenerator plugin body), frames resident in HBM"
+UNIT = "frames/s"
+
+
+def hbm_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json %s)" % k
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    """One 4K pair through the reference's CPU body in a worker process (OpenCV is single-threaded here)."""
+    kind, seed = args
+    import numpy as np
+    synth = importlib.import_module("openfx-opencv_b200.synth")
+    rng = np.random.default_rng(seed)
+    # cheap synthetic pair (workers must not spend their time in the generator): smooth noise + translation
+    base = rng.integers(0, 256, (H4K // 8 + 2, W4K // 8 + 2), dtype=np.uint8).astype(np.float32)
+    base = np.kron(base, np.ones((8, 8), np.float32))[:H4K + 8, :W4K + 8]
+    base = (base[:-8, :-8] + base[8:, 8:] + base[4:-4, 4:-4] * 2) / 4
+    prev = base.astype(np.uint8)
+    nxt = synth.shift_bilinear(prev, 2.5, -1.5)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        import cv2
+        cv2.setNumThreads(1)
+        cv2.calcOpticalFlowFarneback(prev, nxt, None, 0.5, 3, 3, 15, 5, 1.1, 0)
+    else:
+        import oracle
+        oracle.farneback(prev, nxt)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    try:
+        import cv2  # noqa: F401  (the OpenCV the reference plugin calls; un-vendored dependency, pinned 4.13)
+        kind = "reference"
+        what = "cv2.calcOpticalFlowFarneback (OpenCV %s)" % cv2.__version__
+    except Exception:
+        kind = "port"
+        what = "oracle/farneback.c (C restatement)"
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, args.ref_workers))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        def step(i):
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, [(kind, 1000 * i + k) for k in range(workers)])
+            return time.perf_counter() - t0
+        for i in range(args.warmup):
+            step(i)
+        times = [step(100 + i) for i in range(args.steps)]
+    total = sum(times)
+    value = workers * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "farneback_4k", "width": W4K, "height": H4K, "levels": 3, "iterations": 15, "poly_n": 5,
+                   "poly_sigma": 1.1, "winsize": 3, "pairs_per_step": workers},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind,
+                         "sample": "%d worker processes x 1 pair 3840x2160 per step, %s, 1 thread each (host has %d cores)" % (workers, what, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------ our arm
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    pkg = importlib.import_module("openfx-opencv_b200")
+    synth = importlib.import_module("openfx-opencv_b200.synth")
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    ctx = pkg.Context(local)
+    par = pkg.FbParams()
+    W, H, P = args.width, args.height, args.pairs
+    # this rank's shard of the (world*P+1)-frame sequence: contiguous block + one halo frame
+    first, count = seq.shard_range(world * P, world, rank)
+    base = synth.gray(synth.texture(H, W, seed=2000))
+    frames = [synth.shift_bilinear(base, 2.5 * f, -1.5 * f) for f in range(first, first + count + 1)]
+    d_frames = [ctx.to_device(f) for f in frames]
+    d_flows = [ctx.alloc(W * H * 8) for _ in range(count)]
+    h_frames = [ctx.pinned_array((H, W), np.uint8) for _ in frames]
+    for a, b in zip(h_frames, frames):
+        a[...] = b
+    h_flow = ctx.pinned_array((H, W, 2), np.float32)
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        for p in range(count):
+            ctx.farneback_dev(d_frames[p].ptr, d_frames[p + 1].ptr, W, H, d_flows[p].ptr, par)
+
+    def step_e2e():
+        for p in range(count):
+            ctx.farneback(h_frames[p], h_frames[p + 1], par, out=h_flow)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(steps):
+            fn()
+        e1.record(ext)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    ctx.synchronize()
+    ctx.kernel_time_ms(0)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launch_count()
+    ctx.timing(True)
+    ms = timed(step_resident, args.steps)
+    ctx.timing(False)
+    launches = ctx.launch_count() - l0
+    n_iter, iter_ms = ctx.kernel_time_ms(0)
+    clocks = sampler.stop() if sampler else None
+    # the same K steps without the per-kernel events, to show what the instrumentation costs
+    ms_plain = timed(step_resident, args.steps)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        pairs = world * count * args.steps
+        value = pairs / (ms * 1e-3)
+        peak, peak_src = hbm_peak()
+        iter_bytes = pkg.farneback_iter_bytes(W, H, par) * count * args.steps
+        achieved = iter_bytes / (iter_ms * 1e-3) / 1e9 if iter_ms > 0 else 0.0
+        alg = pkg.farneback_algorithmic_bytes(W, H, par)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "farneback_4k" if (W, H) == (W4K, H4K) else "farneback_%dx%d" % (W, H), "width": W, "height": H,
+                       "levels": par.levels, "iterations": par.iterations, "poly_n": par.poly_n, "poly_sigma": par.poly_sigma,
+                       "winsize": par.winsize, "pairs_per_step": world * count, "sharding": "contiguous frame blocks, one per GPU, 1-frame halo",
+                       "l2": "per-pair working set (%.0f MB of M/R/flow planes) exceeds the 126 MB L2; %d distinct pairs rotate" % (
+                           W * H * 68 / 1e6, count),
+                       "algorithmic_gb_per_pair": alg / 1e9},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "fb_band_totals+fb_band (Farneback iteration)", "launches": n_iter, "peak_source": peak_src,
+                         "whole_pair_effective_gbs": alg * pairs / world / (ms * 1e-3) / 1e9,
+                         "whole_pair_frac": alg * pairs / world / (ms * 1e-3) / 1e9 / peak},
+            "e2e": {"value": world * count * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * count,
+                    "d2h_bytes_per_step": 8 * W * H * count, "api": "ofxcv_farneback_u8_host, page-locked host frames"},
+            "gpu_launches": int(lt.item()),
+            "clocks": clocks,
+            "value_without_kernel_events": pairs / (ms_plain * 1e-3),
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                                      "--ref-workers", str(args.ref_workers)], capture_output=True, text=True, timeout=600)
+                ref = json.loads(out.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = ref["cpu_baseline"]
+            except Exception as e:  # the CPU leg must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=W4K)
+    ap.add_argument("--height", type=int, default=H4K)
+    ap.add_argument("--pairs", type=int, default=8, help="frame pairs per GPU per step")
+    ap.add_argument("--ref-workers", type=int, default=64, help="cap on CPU worker processes of the reference arm")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -184,6 +184,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for ptr in getattr(self, "_pinned", []):
+                lib().ofxcv_pinned_free(self.h, ptr)
+            self._pinned = []
             lib().ofxcv_destroy(self.h)
             self.h = None
 
@@ -231,7 +234,19 @@ class Context:
         return int(n), float(ms.value)
 
     # ---- host-buffer entry points (what the OFX glue calls for host-memory clips) ----------------------
-    def farneback(self, prev, nxt, params=None):
+    def pinned_array(self, shape, dtype):
+        """A numpy array over page-locked host memory (ofxcv_pinned_alloc); freed with the context."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = lib().ofxcv_pinned_alloc(self.h, max(n, 1))
+        if not ptr:
+            raise OfxcvError(-3, "ofxcv_pinned_alloc", self.last_error())
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_uint8 * max(n, 1)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def farneback(self, prev, nxt, params=None, out=None):
         """prev, nxt: HxW uint8 (numpy, host).  Returns HxWx2 float32 flow (cv2.calcOpticalFlowFarneback layout)."""
         params = params or FbParams()
         prev = np.ascontiguousarray(prev, np.uint8)
@@ -239,7 +254,8 @@ class Context:
         if prev.ndim != 2 or prev.shape != nxt.shape:
             raise ValueError("prev/next must be equal-shape HxW uint8")
         h, w = prev.shape
-        flow = np.empty((h, w, 2), np.float32)
+        flow = out if out is not None else np.empty((h, w, 2), np.float32)
+        assert flow.shape == (h, w, 2) and flow.dtype == np.float32 and flow.flags.c_contiguous
         st = lib().ofxcv_farneback_u8_host(self.h, _hp(prev), _hp(nxt), w, w, h, _hp(flow), w * 8, C.byref(params))
         self._check(st, "ofxcv_farneback_u8_host")
         return flow

@@ -69,6 +69,16 @@ struct ofxcv_device_guard {
     }
 };
 
+static inline bool ofxcv_is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 static inline int ofxcv_div_up(int a, int b) { return (a + b - 1) / b; }
 
 // workspace slot numbering

@@ -338,7 +338,7 @@ ip_fill(const uint32_t* __restrict__ order, unsigned nfill, uint32_t cnt_base, c
                             float ry = (float)(i - k), rx = (float)(j - l);
                             float vl = rx * rx + ry * ry;
                             float dst = (float)(1. / (vl * sqrt((double)vl)));
-                            float lev = (float)(1. / (1 + fabs(t[n] - ti)));
+                            float lev = (float)(1. / (1 + (double)fabsf(t[n] - ti)));  // f32 difference, f64 sum (C fabs)
                             float dir = rx * gTx + ry * gTy;
                             if (fabs(dir) <= 0.01) dir = 0.000001f;
                             float w = (float)fabs(dst * lev * dir);

@@ -1,0 +1,61 @@
+"""Frame-sequence sharding for the multi-GPU driver.
+
+Frames of a sequence are independent units (inpaint, watershed: one frame; flow: one PAIR), so the sequence is cut
+into contiguous blocks, one per rank, with no data-path collective.  Flow needs frame t+1 for output t, so a rank
+that owns outputs [first, first+count) stages frames [first, first+count] — a one-frame halo
+(VectorGeneratorPlugin::getFramesNeeded, /root/reference/VectorGenerator/VectorGenerator.cpp:675-695).
+torch.distributed is used only for the start/stop barrier and the gather of per-rank results.
+"""
+import numpy as np
+
+
+def shard_range(n_units, world, rank):
+    """(first, count) of the contiguous block of `n_units` outputs owned by `rank` (blocks differ by at most 1)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    base, rem = divmod(n_units, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def frames_needed(first, count, n_frames, forward=True, backward=False):
+    """Indices of the input frames a rank must stage for outputs [first, first+count): its block plus the halo."""
+    lo = first - (1 if backward else 0)
+    hi = first + count - 1 + (1 if forward else 0)
+    return list(range(max(lo, 0), min(hi, n_frames - 1) + 1))
+
+
+def checksum64(arr):
+    """Order-sensitive 64-bit checksum of an output frame (gathered instead of the frames themselves)."""
+    a = np.ascontiguousarray(arr).view(np.uint8).ravel().astype(np.uint64)
+    idx = np.arange(1, a.size + 1, dtype=np.uint64)
+    return int((a * (idx * np.uint64(0x9E3779B97F4A7C15) | np.uint64(1))).sum(dtype=np.uint64))
+
+
+def gather_results(local, group=None):
+    """all_gather of small per-rank python results (frame ranges, checksums, timings) to every rank."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return [local]
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, local, group=group)
+    return out
+
+
+def run_sharded(n_units, process_unit, world=None, rank=None):
+    """Run process_unit(i) -> small result for every unit of this rank's block, barrier on both sides, and return
+    the results of ALL ranks in unit order (on every rank)."""
+    import torch.distributed as dist
+    inited = dist.is_available() and dist.is_initialized()
+    world = world if world is not None else (dist.get_world_size() if inited else 1)
+    rank = rank if rank is not None else (dist.get_rank() if inited else 0)
+    first, count = shard_range(n_units, world, rank)
+    if inited:
+        dist.barrier()
+    mine = [(i, process_unit(i)) for i in range(first, first + count)]
+    if inited:
+        dist.barrier()
+    merged = {}
+    for part in gather_results(mine):
+        merged.update(dict(part))
+    return [merged[i] for i in range(n_units)]

@@ -1,0 +1,67 @@
+"""Host-side logic of the multi-GPU sequence driver, exercised with world_size-2 gloo on CPU."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions_everything():
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    for n in (0, 1, 7, 8, 300, 1000):
+        for world in (1, 2, 3, 4, 8):
+            got = []
+            for r in range(world):
+                first, count = seq.shard_range(n, world, r)
+                got += list(range(first, first + count))
+                assert count in (n // world, n // world + 1)
+            assert got == list(range(n))
+    assert seq.frames_needed(4, 4, 20) == [4, 5, 6, 7, 8]            # forward flow: +1 halo frame
+    assert seq.frames_needed(4, 4, 20, backward=True) == [3, 4, 5, 6, 7, 8]
+    assert seq.frames_needed(16, 4, 20) == [16, 17, 18, 19]          # clamped at the sequence end
+    with pytest.raises(ValueError):
+        seq.shard_range(4, 2, 2)
+
+
+def _worker(rank, world, port, n_units, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+
+    def unit(i):  # stands for "render output frame i and checksum it"
+        rng = np.random.default_rng(i)
+        return (rank, seq.checksum64(rng.integers(0, 255, (16, 16), dtype=np.uint8)))
+
+    res = seq.run_sharded(n_units, unit)
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)   # the bench's max-over-ranks timing reduction
+    q.put((rank, res, float(t.item())))
+    dist.destroy_process_group()
+
+
+def test_run_sharded_gloo_world2():
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_units, world, port = 7, 2, 29517 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_units, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [seq.checksum64(np.random.default_rng(i).integers(0, 255, (16, 16), dtype=np.uint8)) for i in range(n_units)]
+    for rank, res, tmax in outs:
+        assert [c for _, c in res] == expect          # every rank sees every unit's result, in order
+        owners = [o for o, _ in res]
+        assert owners == [0, 0, 0, 0, 1, 1, 1]        # contiguous blocks
+        assert tmax == 2.0
