@@ -163,6 +163,11 @@ OFXCV_API int ofxcv_rgba8_to_rgb8_mask(ofxcv_ctx* ctx, ofxcv_stream stream, cons
 /* RGB8 -> RGBA8 with alpha 255: the write-back loop inpaint.cpp:320-358 / segment.cpp:307-323. */
 OFXCV_API int ofxcv_rgb8_to_rgba8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb, ptrdiff_t rgb_stride,
                                   uint8_t* rgba, ptrdiff_t rgba_stride, int W, int H);
+/* the same write-back with the plugin's optional noise on hole pixels (inpaint.cpp:320-347, `inpaintnoise`):
+ * noise_div = (int)(1/inpaintnoise), 0 = no noise.  Counter-based RNG (documented, outside the parity contract). */
+OFXCV_API int ofxcv_rgb8_to_rgba8_noise(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb, ptrdiff_t rgb_stride,
+                                        const uint8_t* mask, ptrdiff_t mask_stride, uint8_t* rgba, ptrdiff_t rgba_stride,
+                                        int W, int H, int noise_div, unsigned seed);
 /* deterministic seed grid for the segment plugin (`seeds` param): n = gx*gy squares of
  * (2*half+1)^2 pixels labelled 1..n on a regular grid, 0 elsewhere. */
 OFXCV_API int ofxcv_seed_grid(ofxcv_ctx* ctx, ofxcv_stream stream, int32_t* markers, ptrdiff_t markers_stride,

@@ -104,6 +104,7 @@ def lib():
         "ofxcv_flow_to_rgba32f": (i, [vp, vp, vp, pd, vp, pd, i, i, C.POINTER(C.c_int), d, d]),
         "ofxcv_rgba8_to_rgb8_mask": (i, [vp, vp, vp, pd, vp, pd, vp, pd, i, i, i]),
         "ofxcv_rgb8_to_rgba8": (i, [vp, vp, vp, pd, vp, pd, i, i]),
+        "ofxcv_rgb8_to_rgba8_noise": (i, [vp, vp, vp, pd, vp, pd, vp, pd, i, i, i, C.c_uint]),
         "ofxcv_seed_grid": (i, [vp, vp, vp, pd, i, i, i, i, i]),
         "ofxcv_labels_to_rgba8": (i, [vp, vp, vp, pd, vp, pd, vp, pd, i, i, i]),
     }

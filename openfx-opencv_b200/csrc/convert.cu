@@ -141,6 +141,34 @@ __global__ void __launch_bounds__(256) cv_rgb_to_rgba(const uint8_t* __restrict_
     q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; q[3] = 255;
 }
 
+// write-back with the optional "camera noise" of inpaint.cpp:320-347: on hole pixels whose x is a multiple of 4,
+// a = ((r % 10) - 5) / noise_div is added to the three colour bytes.  The reference draws r from libc rand()
+// reseeded from pixel data (not reproducible across libcs: SURVEY.md B5); here r is a counter-based hash of
+// (x, y, seed) -- same amplitude and spatial pattern, documented as outside the parity contract.
+__device__ __forceinline__ unsigned cv_hash(unsigned x, unsigned y, unsigned s)
+{
+    unsigned h = x * 0x9E3779B1u ^ (y + 0x7F4A7C15u) * 0x85EBCA77u ^ (s + 1u) * 0xC2B2AE3Du;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
+}
+__global__ void __launch_bounds__(256) cv_rgb_to_rgba_noise(const uint8_t* __restrict__ rgb, ptrdiff_t rgb_stride,
+                                                            const uint8_t* __restrict__ mask, ptrdiff_t mask_stride,
+                                                            uint8_t* __restrict__ rgba, ptrdiff_t rgba_stride, int W, int H,
+                                                            int noise_div, unsigned seed)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    const uint8_t* p = rgb + (size_t)y * rgb_stride + 3 * (size_t)x;
+    uint8_t* q = rgba + (size_t)y * rgba_stride + 4 * (size_t)x;
+    int a = 0;
+    if (noise_div > 0 && (x & 3) == 0 && mask[(size_t)y * mask_stride + x]) a = ((int)(cv_hash(x, y, seed) % 10u) - 5) / noise_div;
+    q[0] = (uint8_t)min(max((int)p[0] + a, 0), 255);
+    q[1] = (uint8_t)min(max((int)p[1] + a, 0), 255);
+    q[2] = (uint8_t)min(max((int)p[2] + a, 0), 255);
+    q[3] = 255;
+}
+
 __global__ void __launch_bounds__(256) cv_seed_grid(int32_t* __restrict__ m, ptrdiff_t ms, int W, int H, int gx, int gy, int half)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,6 +288,18 @@ int ofxcv_rgb8_to_rgba8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb,
     if (!rgb || !rgba || W <= 0 || H <= 0) return OFXCV_ERR_BAD_ARG;
     ofxcv_device_guard guard(ctx->device);
     cv_rgb_to_rgba<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, pick(ctx, stream)>>>(rgb, rgb_stride, rgba, rgba_stride, W, H);
+    OFXCV_LAUNCH_CHECK(ctx);
+    return OFXCV_OK;
+}
+
+int ofxcv_rgb8_to_rgba8_noise(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb, ptrdiff_t rgb_stride, const uint8_t* mask,
+                              ptrdiff_t mask_stride, uint8_t* rgba, ptrdiff_t rgba_stride, int W, int H, int noise_div, unsigned seed)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!rgb || !rgba || W <= 0 || H <= 0 || (noise_div > 0 && !mask)) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    cv_rgb_to_rgba_noise<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, pick(ctx, stream)>>>(rgb, rgb_stride, mask, mask_stride, rgba, rgba_stride,
+                                                                                       W, H, noise_div, seed);
     OFXCV_LAUNCH_CHECK(ctx);
     return OFXCV_OK;
 }
