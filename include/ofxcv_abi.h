@@ -61,6 +61,11 @@ OFXCV_API uint64_t ofxcv_launch_count(const ofxcv_ctx* ctx);
  * family 0 = Farneback iteration kernel, 1 = inpaint fill, 2 = watershed flood.  Returns launches counted. */
 OFXCV_API uint64_t ofxcv_kernel_time_ms(ofxcv_ctx* ctx, int family, double* total_ms);
 OFXCV_API void ofxcv_kernel_time_enable(ofxcv_ctx* ctx, int enable);
+/* developer profile: while enabled every labelled launch is bracketed by CUDA events on its stream;
+ * ofxcv_prof_report writes "name tag launches total_ms" lines (tag = pyramid scale for Farneback) into buf,
+ * returns the full text length and resets the records. */
+OFXCV_API void ofxcv_prof_enable(ofxcv_ctx* ctx, int enable);
+OFXCV_API size_t ofxcv_prof_report(ofxcv_ctx* ctx, char* buf, size_t cap);
 
 /* plain device-memory helpers so that a non-CUDA host language (ctypes, cgo, JNI) can stage frames */
 OFXCV_API void* ofxcv_device_alloc(ofxcv_ctx* ctx, size_t bytes);

@@ -76,6 +76,8 @@ def lib():
         "ofxcv_launch_count": (C.c_uint64, [vp]),
         "ofxcv_kernel_time_ms": (C.c_uint64, [vp, i, C.POINTER(C.c_double)]),
         "ofxcv_kernel_time_enable": (None, [vp, i]),
+        "ofxcv_prof_enable": (None, [vp, i]),
+        "ofxcv_prof_report": (sz, [vp, C.c_char_p, sz]),
         "ofxcv_device_alloc": (vp, [vp, sz]),
         "ofxcv_device_free": (None, [vp, vp]),
         "ofxcv_pinned_alloc": (vp, [vp, sz]),
@@ -233,6 +235,19 @@ class Context:
         ms = C.c_double(0)
         n = lib().ofxcv_kernel_time_ms(self.h, family, C.byref(ms))
         return int(n), float(ms.value)
+
+    def prof(self, enable):
+        lib().ofxcv_prof_enable(self.h, 1 if enable else 0)
+
+    def prof_report(self):
+        """[(name, tag, launches, total_ms)] of the labelled launches since the last report."""
+        buf = C.create_string_buffer(1 << 16)
+        lib().ofxcv_prof_report(self.h, buf, len(buf))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, tag, n, ms = line.split()
+            rows.append((name, int(tag), int(n), float(ms)))
+        return rows
 
     # ---- host-buffer entry points (what the OFX glue calls for host-memory clips) ----------------------
     def pinned_array(self, shape, dtype):

@@ -34,6 +34,14 @@ struct ofxcv_ctx {
     std::vector<ofxcv_timed_launch> event_pool;
     double timed_ms[3] = {0, 0, 0};
     uint64_t timed_n[3] = {0, 0, 0};
+    // per-launch profile (tools/prof_*.py): one event pair per labelled launch, aggregated by ofxcv_prof_report
+    bool prof_on = false;
+    struct prof_rec {
+        const char* name;
+        int tag;
+        cudaEvent_t a, b;
+    };
+    std::vector<prof_rec> prof;
     int64_t inpaint_stats[4] = {0, 0, 0, 0};
     int64_t watershed_stats[4] = {0, 0, 0, 0};
 };
@@ -43,6 +51,34 @@ void* ofxcv_ws(ofxcv_ctx* ctx, int slot, size_t bytes);    // device workspace s
 void* ofxcv_pin(ofxcv_ctx* ctx, int slot, size_t bytes);   // pinned host slot
 void ofxcv_time_begin(ofxcv_ctx* ctx, int family, cudaStream_t s);
 void ofxcv_time_end(ofxcv_ctx* ctx, int family, cudaStream_t s);
+
+// RAII label around one or more launches on stream s; free when profiling is off
+struct ofxcv_prof_scope {
+    ofxcv_ctx* ctx;
+    cudaStream_t s;
+    bool on;
+    ofxcv_prof_scope(ofxcv_ctx* c, cudaStream_t st, const char* name, int tag) : ctx(c), s(st), on(c->prof_on)
+    {
+        if (!on) return;
+        ofxcv_ctx::prof_rec r;
+        r.name = name;
+        r.tag = tag;
+        if (!ctx->event_pool.empty()) {
+            r.a = ctx->event_pool.back().a;
+            r.b = ctx->event_pool.back().b;
+            ctx->event_pool.pop_back();
+        } else {
+            cudaEventCreate(&r.a);
+            cudaEventCreate(&r.b);
+        }
+        cudaEventRecord(r.a, s);
+        ctx->prof.push_back(r);
+    }
+    ~ofxcv_prof_scope()
+    {
+        if (on) cudaEventRecord(ctx->prof.back().b, s);
+    }
+};
 
 #define OFXCV_CUDA(ctx, call)                                         \
     do {                                                              \

@@ -135,6 +135,10 @@ void ofxcv_destroy(ofxcv_ctx* ctx)
             cudaEventDestroy(t.a);
             cudaEventDestroy(t.b);
         }
+    for (auto& r : ctx->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
     for (auto& t : ctx->event_pool) {
         cudaEventDestroy(t.a);
         cudaEventDestroy(t.b);
@@ -183,6 +187,55 @@ uint64_t ofxcv_kernel_time_ms(ofxcv_ctx* ctx, int family, double* total_ms)
     ctx->timed_ms[family] = 0;
     ctx->timed_n[family] = 0;
     return n;
+}
+
+void ofxcv_prof_enable(ofxcv_ctx* ctx, int enable)
+{
+    if (ctx) ctx->prof_on = enable != 0;
+}
+
+size_t ofxcv_prof_report(ofxcv_ctx* ctx, char* buf, size_t cap)
+{
+    if (!ctx) return 0;
+    ofxcv_device_guard g(ctx->device);
+    struct agg {
+        const char* name;
+        int tag;
+        double ms;
+        uint64_t n;
+    };
+    std::vector<agg> rows;
+    for (auto& r : ctx->prof) {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+        bool found = false;
+        for (auto& a : rows)
+            if (a.tag == r.tag && !strcmp(a.name, r.name)) {
+                a.ms += ms;
+                a.n++;
+                found = true;
+                break;
+            }
+        if (!found) rows.push_back({r.name, r.tag, ms, 1});
+        ofxcv_timed_launch t;
+        t.a = r.a;
+        t.b = r.b;
+        ctx->event_pool.push_back(t);
+    }
+    ctx->prof.clear();
+    std::string out;
+    char line[256];
+    for (auto& a : rows) {
+        snprintf(line, sizeof line, "%s %d %llu %.6f\n", a.name, a.tag, (unsigned long long)a.n, a.ms);
+        out += line;
+    }
+    if (buf && cap) {
+        size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return out.size();
 }
 
 void* ofxcv_device_alloc(ofxcv_ctx* ctx, size_t bytes)
