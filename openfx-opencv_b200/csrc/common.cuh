@@ -149,7 +149,8 @@ enum {
     WS_INP_G,
     WS_INP_H,
     WS_FB_SINT,  // per-band interior difference sums of the running column sum
-    WS_FB_TOT,   // per-band totals
+    WS_FB_TOT,   // per-band totals / exclusive prefixes (ping-pong)
+    WS_FB_CNT,   // per-strip finish tickets of the band kernel
     WS_COUNT
 };
 static_assert(WS_COUNT <= 32, "workspace slots");
