@@ -11,9 +11,12 @@ sharded one block per GPU with no data-path collective (weak scaling: per-GPU wo
            max over ranks, barrier + synchronize on both sides;
   e2e    = the same metric through the host-buffer C-ABI call (ofxcv_farneback_u8_host) with page-locked host
            frames: H2D of both frames and D2H of the flow field inside the timed region, every step;
-  roofline = the Farneback iteration kernels (fb_band_totals + fb_band): algorithmic bytes (88 B per scale-pixel
-           per iteration, 28 for the last one: SURVEY.md 8d) / their CUDA-event time inside the timed region,
-           against the measured HBM copy peak in MEASURED_PEAKS.json (fallback 6650 GB/s);
+  roofline = the dominant kernel, fb_band3<ITER> at full resolution (14 of the 16 band launches of scale 0):
+           algorithmic bytes per launch (88 B per pixel: SURVEY.md 8d) / its average CUDA-event duration inside the
+           timed region, against the measured HBM copy peak in MEASURED_PEAKS.json (fallback 6650 GB/s); `traffic` =
+           dram bytes read+written per launch from the committed `ncu --set full` capture (profiles/*.json);
+  plugins = the other two plugin bodies at 4K on the same GPU (rank 0, N=1 only): NS / Telea inpaint 10 % mask and
+           watershed 256 seeds, frames resident in HBM, with their CPU reference (cv2) timed beside them;
   cpu_baseline = the reference arm run once on this box's host cores on a bounded sample (rank 0, N=1 only).
 """
 import argparse
@@ -44,6 +47,20 @@ def hbm_peak():
     except Exception:
         pass
     return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic(W, H):
+    """dram bytes (read + write) per launch of the dominant kernel from the newest committed ncu summary."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_fb_band3.json"))):
+        try:
+            d = json.load(open(f))
+            if d.get("width") == W and d.get("height") == H:
+                best = (float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), os.path.relpath(f, ROOT))
+        except Exception:
+            pass
+    return best if best else (None, None)
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -235,8 +252,9 @@ def run_ours(args):
         pairs = world * count * args.steps
         value = pairs / (ms * 1e-3)
         peak, peak_src = hbm_peak()
-        iter_bytes = pkg.farneback_iter_bytes(W, H, par) * count * args.steps
-        achieved = iter_bytes / (iter_ms * 1e-3) / 1e9 if iter_ms > 0 else 0.0
+        launch_bytes = pkg.farneback_iter_bytes(W, H, par)
+        achieved = launch_bytes * n_iter / (iter_ms * 1e-3) / 1e9 if iter_ms > 0 else 0.0
+        traffic, traffic_src = ncu_traffic(W, H)
         alg = pkg.farneback_algorithmic_bytes(W, H, par)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -248,8 +266,10 @@ def run_ours(args):
                        "l2": "per-pair working set (%.0f MB of M/R/flow planes) exceeds the 126 MB L2; %d distinct pairs rotate" % (
                            W * H * 68 / 1e6, count),
                        "algorithmic_gb_per_pair": alg / 1e9},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "fb_band_totals+fb_band (Farneback iteration)", "launches": n_iter, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "fb_band3<ITER> at %dx%d (full-resolution Farneback iteration launches)" % (W, H), "launches": n_iter,
+                         "us_per_launch": 1e3 * iter_ms / max(n_iter, 1), "algorithmic_bytes_per_launch": launch_bytes,
+                         "traffic_source": traffic_src, "peak_source": peak_src,
                          "whole_pair_effective_gbs": alg * pairs / world / (ms * 1e-3) / 1e9,
                          "whole_pair_frac": alg * pairs / world / (ms * 1e-3) / 1e9 / peak},
             "e2e": {"value": world * count * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * count,
@@ -266,12 +286,78 @@ def run_ours(args):
                 line["cpu_baseline"] = ref["cpu_baseline"]
             except Exception as e:  # the CPU leg must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        if world == 1 and not args.no_plugins:
+            try:
+                line["plugins"] = bench_plugins(pkg, synth, ctx, W, H, not args.no_cpu)
+            except Exception as e:
+                line["plugins"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
     return 0
+
+
+def bench_plugins(pkg, synth, ctx, W, H, with_cpu):
+    """The other two plugin bodies at the bench resolution: frames resident in HBM, wall-clock around a synchronise
+    (these bodies are many launches each); CPU = cv2 on one host core (they are single-threaded algorithms)."""
+    import numpy as np
+    out = {}
+    img = synth.texture(H, W, seed=4)
+    mask = synth.iid_mask(H, W, 1000, 0.10)
+    d_img, d_mask, d_out = ctx.to_device(img), ctx.to_device(mask), ctx.alloc(W * H * 3)
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+    except Exception:
+        cv2 = None
+
+    def gpu_time(fn, n):
+        fn(); ctx.synchronize()
+        t = time.perf_counter()
+        for _ in range(n):
+            fn()
+        ctx.synchronize()
+        return (time.perf_counter() - t) / n
+
+    for name, method in (("inpaint_ns", pkg.INPAINT_NS), ("inpaint_telea", pkg.INPAINT_TELEA)):
+        dt = gpu_time(lambda: ctx.inpaint_dev(d_img.ptr, 3, d_mask.ptr, d_out.ptr, W, H, 3.0, method), 3)
+        ent = {"value": 1 / dt, "unit": "frames/s", "ms_per_frame": dt * 1e3, "workload": "%dx%d RGB8, 10%% iid mask, radius 3" % (W, H),
+               "algorithmic_gbs": 7.0 * W * H / dt / 1e9, "bound": "latency (FMM order), not HBM"}
+        if cv2 is not None and with_cpu:
+            t = time.perf_counter()
+            ref = cv2.inpaint(img, mask, 3.0, cv2.INPAINT_NS if method == pkg.INPAINT_NS else cv2.INPAINT_TELEA)
+            ent["cpu_frames_per_s"] = 1 / (time.perf_counter() - t)
+            got = d_out.download((H, W, 3), np.uint8)
+            ent["bytes_differing_from_cv2"] = int((got != ref).sum())
+        out[name] = ent
+    mk = synth.seed_markers(H, W, 256, 5)
+    for nf in (1, 64):
+        d_rgbs, d_mks = ctx.alloc(W * H * 3 * nf), ctx.alloc(W * H * 4 * nf)
+        L = pkg.lib()
+        for f in range(nf):
+            L.ofxcv_upload(ctx.h, None, d_rgbs.ptr + f * W * H * 3, img.ctypes.data, W * H * 3)
+            L.ofxcv_upload(ctx.h, None, d_mks.ptr + f * W * H * 4, mk.ctypes.data, W * H * 4)
+        ctx.synchronize()
+        t = time.perf_counter()
+        ctx.watershed_dev(d_rgbs.ptr, d_mks.ptr, W, H, nf)
+        ctx.synchronize()
+        dt = time.perf_counter() - t
+        ent = {"value": nf / dt, "unit": "frames/s", "frames_in_flight": nf, "ms_total": dt * 1e3, "workload": "%dx%d RGB8, 256 seeds" % (W, H),
+               "algorithmic_gbs": 11.0 * W * H * nf / dt / 1e9, "bound": "latency (ordered flood), not HBM"}
+        if nf == 1 and cv2 is not None and with_cpu:
+            m = mk.copy()
+            t = time.perf_counter()
+            cv2.watershed(img, m)
+            ent["cpu_frames_per_s"] = 1 / (time.perf_counter() - t)
+            got = np.empty((H, W), np.int32)
+            L.ofxcv_download(ctx.h, None, got.ctypes.data, d_mks.ptr, W * H * 4)
+            ctx.synchronize()
+            ent["labels_differing_from_cv2"] = int((got != m).sum())
+        out["watershed_%dframes" % nf] = ent
+        d_rgbs.free(); d_mks.free()
+    return out
 
 
 def main():
@@ -285,6 +371,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=8, help="frame pairs per GPU per step")
     ap.add_argument("--ref-workers", type=int, default=64, help="cap on CPU worker processes of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-plugins", action="store_true", help="skip the inpaint / watershed lines")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

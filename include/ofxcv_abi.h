@@ -58,7 +58,8 @@ OFXCV_API const char* ofxcv_last_error(const ofxcv_ctx* ctx); /* text of the las
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches claim) */
 OFXCV_API uint64_t ofxcv_launch_count(const ofxcv_ctx* ctx);
 /* device-time (ms, CUDA events on the launching stream) of the dominant kernel family since the last reset:
- * family 0 = Farneback iteration kernel, 1 = inpaint fill, 2 = watershed flood.  Returns launches counted. */
+ * family 0 = Farneback band kernel, full-resolution ITER launches; 1 = inpaint fill; 2 = watershed flood.
+ * Returns launches counted. */
 OFXCV_API uint64_t ofxcv_kernel_time_ms(ofxcv_ctx* ctx, int family, double* total_ms);
 OFXCV_API void ofxcv_kernel_time_enable(ofxcv_ctx* ctx, int enable);
 /* developer profile: while enabled every labelled launch is bracketed by CUDA events on its stream;
@@ -95,8 +96,9 @@ OFXCV_API void ofxcv_fb_default_params(ofxcv_fb_params* p);
  * (SURVEY.md section 8d byte model: sum_k n_k*(66+88*I) + 2*W*H per scale). */
 OFXCV_API int ofxcv_farneback_scales(int W, int H, const ofxcv_fb_params* p);
 OFXCV_API double ofxcv_farneback_algorithmic_bytes(int W, int H, const ofxcv_fb_params* p);
-/* algorithmic bytes handled by the iteration-kernel launches alone (88 B per scale-pixel per iteration,
- * 28 for the last one) -- the numerator of bench.py's roofline for the dominant kernel. */
+/* algorithmic bytes of ONE full-resolution iteration launch of the band kernel (88 B per pixel: SURVEY.md 8d) --
+ * the numerator of bench.py's roofline for the dominant kernel; ofxcv_kernel_time_ms(ctx, 0, ..) times exactly
+ * those launches (iterations-1 per pair). */
 OFXCV_API double ofxcv_farneback_iter_bytes(int W, int H, const ofxcv_fb_params* p);
 OFXCV_API size_t ofxcv_farneback_workspace_bytes(int W, int H, const ofxcv_fb_params* p);
 
