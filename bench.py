@@ -9,8 +9,8 @@ default plugin parameters: levels 3, winsize 3, 15 iterations, polyN 5, sigma 1.
 sharded one block per GPU with no data-path collective (weak scaling: per-GPU work is fixed).
   value  = flow fields (frame pairs) per second, whole job, frames already resident in HBM, CUDA-event timed,
            max over ranks, barrier + synchronize on both sides;
-  e2e    = the same metric through the host-buffer C-ABI call (ofxcv_farneback_u8_host) with page-locked host
-           frames: H2D of both frames and D2H of the flow field inside the timed region, every step;
+  e2e    = the same metric through the host-buffer C-ABI call (ofxcv_farneback_sequence_u8_host) with page-locked host
+           frames: H2D of every frame and D2H of every flow field inside the timed region, every step;
   roofline = the dominant kernel, fb_band3<ITER> at full resolution (14 of the 16 band launches of scale 0):
            algorithmic bytes per launch (88 B per pixel: SURVEY.md 8d) / its average CUDA-event duration inside the
            timed region, against the measured HBM copy peak in MEASURED_PEAKS.json (fallback 6650 GB/s); `traffic` =
@@ -189,12 +189,12 @@ def run_ours(args):
     first, count = seq.shard_range(world * P, world, rank)
     base = synth.gray(synth.texture(H, W, seed=2000))
     frames = [synth.shift_bilinear(base, 2.5 * f, -1.5 * f) for f in range(first, first + count + 1)]
-    d_frames = [ctx.to_device(f) for f in frames]
-    d_flows = [ctx.alloc(W * H * 8) for _ in range(count)]
+    d_frames = ctx.to_device(np.stack(frames))          # the rank's clip block, contiguous in HBM
+    d_flows = ctx.alloc(W * H * 8 * count)
     h_frames = [ctx.pinned_array((H, W), np.uint8) for _ in frames]
     for a, b in zip(h_frames, frames):
         a[...] = b
-    h_flow = ctx.pinned_array((H, W, 2), np.float32)
+    h_flows = [ctx.pinned_array((H, W, 2), np.float32) for _ in range(count)]
     ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
 
     def barrier():
@@ -204,13 +204,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # one step = one pass over the rank's clip block through the sequence entry points: every frame is blurred and
+    # expanded ONCE per pass (frame t+1 of pair t is frame t of pair t+1), nothing is carried from step to step
     def step_resident():
-        for p in range(count):
-            ctx.farneback_dev(d_frames[p].ptr, d_frames[p + 1].ptr, W, H, d_flows[p].ptr, par)
+        ctx.farneback_sequence_dev(d_frames.ptr, W, H, count + 1, d_flows.ptr, par)
 
     def step_e2e():
-        for p in range(count):
-            ctx.farneback(h_frames[p], h_frames[p + 1], par, out=h_flow)
+        ctx.farneback_sequence(h_frames, par, out=h_flows)
 
     def timed(fn, steps):
         barrier()
@@ -263,6 +263,7 @@ def run_ours(args):
             "config": {"workload": "farneback_4k" if (W, H) == (W4K, H4K) else "farneback_%dx%d" % (W, H), "width": W, "height": H,
                        "levels": par.levels, "iterations": par.iterations, "poly_n": par.poly_n, "poly_sigma": par.poly_sigma,
                        "winsize": par.winsize, "pairs_per_step": world * count, "sharding": "contiguous frame blocks, one per GPU, 1-frame halo",
+                       "call": "ofxcv_farneback_sequence_u8 (one clip block of pairs_per_step/n_gpus + 1 frames per step; each frame's pyramid built once per step)",
                        "l2": "per-pair working set (%.0f MB of M/R/flow planes) exceeds the 126 MB L2; %d distinct pairs rotate" % (
                            W * H * 68 / 1e6, count),
                        "algorithmic_gb_per_pair": alg / 1e9},
@@ -272,8 +273,9 @@ def run_ours(args):
                          "traffic_source": traffic_src, "peak_source": peak_src,
                          "whole_pair_effective_gbs": alg * pairs / world / (ms * 1e-3) / 1e9,
                          "whole_pair_frac": alg * pairs / world / (ms * 1e-3) / 1e9 / peak},
-            "e2e": {"value": world * count * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * count,
-                    "d2h_bytes_per_step": 8 * W * H * count, "api": "ofxcv_farneback_u8_host, page-locked host frames"},
+            "e2e": {"value": world * count * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W * H * (count + 1),
+                    "d2h_bytes_per_step": 8 * W * H * count,
+                    "api": "ofxcv_farneback_sequence_u8_host, page-locked host frames, upload/compute/download on three streams"},
             "gpu_launches": int(lt.item()),
             "clocks": clocks,
             "value_without_kernel_events": pairs / (ms_plain * 1e-3),

@@ -110,6 +110,34 @@ OFXCV_API int ofxcv_farneback_u8_host(ofxcv_ctx* ctx, const uint8_t* prev, const
                                       int W, int H, float* flow, ptrdiff_t flow_stride,
                                       const ofxcv_fb_params* params);
 
+/* The same call with frame keys: a non-zero key names the CONTENT of a frame (the caller guarantees that equal keys
+ * mean equal pixels, size and parameters); the context keeps the polynomial-expansion pyramids of the last few
+ * keyed frames, so that frame t+1 of pair t is not blurred / expanded again as frame t of pair t+1 (or for the
+ * backward flow of the same render: VectorGenerator.cpp:559-638 runs t->t+1 and t->t-1).  Calls that share keys
+ * must be issued on the same stream.  key 0 = anonymous (what ofxcv_farneback_u8 passes). */
+OFXCV_API int ofxcv_farneback_u8_keyed(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, const uint8_t* next,
+                                       ptrdiff_t stride, int W, int H, float* flow, ptrdiff_t flow_stride,
+                                       const ofxcv_fb_params* params, uint64_t key_prev, uint64_t key_next);
+/* a content key for the call above: 64-bit position-sensitive hash of a device-resident 8-bit plane (never 0).
+ * Synchronises `stream`.  The VectorGenerator glue keys every staged gray frame with it, so that consecutive
+ * renders of a clip (and the forward / backward flow of one render) share frame pyramids. */
+OFXCV_API int ofxcv_content_key_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* img, ptrdiff_t stride, int W,
+                                   int H, uint64_t* key);
+OFXCV_API void ofxcv_farneback_cache_clear(ofxcv_ctx* ctx);
+/* pyramids built / cache hits since the context was created */
+OFXCV_API int ofxcv_farneback_cache_stats(const ofxcv_ctx* ctx, uint64_t* built, uint64_t* hits);
+/* A clip: nframes gray frames (frame t at frames + t*frame_stride) -> nframes-1 forward flow fields t -> t+1
+ * (flow t at flows + t*flow_frame_stride bytes).  Every frame's pyramid is built exactly once per call.  The host
+ * flavour takes arrays of host pointers (page-locked for real overlap) and pipelines upload / compute / download
+ * on three streams; this is the call of a host that renders a sequence (BASELINE.json configs 4 and 5). */
+OFXCV_API int ofxcv_farneback_sequence_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* frames, ptrdiff_t stride,
+                                          size_t frame_stride, int W, int H, int nframes, float* flows,
+                                          ptrdiff_t flow_stride, size_t flow_frame_stride,
+                                          const ofxcv_fb_params* params);
+OFXCV_API int ofxcv_farneback_sequence_u8_host(ofxcv_ctx* ctx, const uint8_t* const* frames, ptrdiff_t stride, int W,
+                                               int H, int nframes, float* const* flows, ptrdiff_t flow_stride,
+                                               const ofxcv_fb_params* params);
+
 /* ---- inpainting ------------------------------------------------------------------------------------- */
 /* Replaces cvInpaint(image0, mask, image1, radius, CV_INPAINT_TELEA) at
  * /root/reference/opencv2fx/inpaint/inpaint.cpp:311-318 (Telea hard-wired at :311; Navier-Stokes is the

@@ -92,6 +92,12 @@ def lib():
         "ofxcv_farneback_workspace_bytes": (sz, [i, i, fbp]),
         "ofxcv_farneback_u8": (i, [vp, vp, vp, vp, pd, i, i, vp, pd, fbp]),
         "ofxcv_farneback_u8_host": (i, [vp, vp, vp, pd, i, i, vp, pd, fbp]),
+        "ofxcv_farneback_u8_keyed": (i, [vp, vp, vp, vp, pd, i, i, vp, pd, fbp, C.c_uint64, C.c_uint64]),
+        "ofxcv_content_key_u8": (i, [vp, vp, vp, pd, i, i, C.POINTER(C.c_uint64)]),
+        "ofxcv_farneback_cache_clear": (None, [vp]),
+        "ofxcv_farneback_cache_stats": (i, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "ofxcv_farneback_sequence_u8": (i, [vp, vp, vp, pd, sz, i, i, i, vp, pd, sz, fbp]),
+        "ofxcv_farneback_sequence_u8_host": (i, [vp, C.POINTER(vp), pd, i, i, i, C.POINTER(vp), pd, fbp]),
         "ofxcv_inpaint_u8": (i, [vp, vp, vp, pd, i, vp, pd, vp, pd, i, i, d, i]),
         "ofxcv_inpaint_u8_host": (i, [vp, vp, pd, i, vp, pd, vp, pd, i, i, d, i]),
         "ofxcv_inpaint_workspace_bytes": (sz, [i, i, i]),
@@ -321,6 +327,40 @@ class Context:
         params = params or FbParams()
         st = lib().ofxcv_farneback_u8(self.h, stream, prev_d, next_d, stride or w, w, h, flow_d, flow_stride or w * 8, C.byref(params))
         self._check(st, "ofxcv_farneback_u8")
+
+    def farneback_keyed_dev(self, prev_d, next_d, w, h, flow_d, key_prev, key_next, params=None, stream=None):
+        params = params or FbParams()
+        st = lib().ofxcv_farneback_u8_keyed(self.h, stream, prev_d, next_d, w, w, h, flow_d, w * 8, C.byref(params), key_prev, key_next)
+        self._check(st, "ofxcv_farneback_u8_keyed")
+
+    def content_key(self, img_d, w, h):
+        k = C.c_uint64(0)
+        self._check(lib().ofxcv_content_key_u8(self.h, None, img_d, w, w, h, C.byref(k)), "ofxcv_content_key_u8")
+        return int(k.value)
+
+    def farneback_cache_stats(self):
+        b, h = C.c_uint64(0), C.c_uint64(0)
+        self._check(lib().ofxcv_farneback_cache_stats(self.h, C.byref(b), C.byref(h)), "ofxcv_farneback_cache_stats")
+        return int(b.value), int(h.value)
+
+    def farneback_sequence_dev(self, frames_d, w, h, nframes, flows_d, params=None, stream=None):
+        """frames_d: nframes contiguous HxW u8 frames on the device; flows_d: nframes-1 contiguous HxWx2 f32 fields."""
+        params = params or FbParams()
+        st = lib().ofxcv_farneback_sequence_u8(self.h, stream, frames_d, w, w * h, w, h, nframes, flows_d, w * 8, w * h * 8, C.byref(params))
+        self._check(st, "ofxcv_farneback_sequence_u8")
+
+    def farneback_sequence(self, frames, params=None, out=None):
+        """frames: list of HxW uint8 host arrays (page-locked ones overlap copies with compute).  Returns the list of
+        len(frames)-1 HxWx2 float32 flow fields (written into `out` when given)."""
+        params = params or FbParams()
+        h, w = frames[0].shape
+        n = len(frames)
+        flows = out if out is not None else [np.empty((h, w, 2), np.float32) for _ in range(n - 1)]
+        fp = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        op = (C.c_void_p * (n - 1))(*[f.ctypes.data for f in flows])
+        st = lib().ofxcv_farneback_sequence_u8_host(self.h, fp, w, w, h, n, op, w * 8, C.byref(params))
+        self._check(st, "ofxcv_farneback_sequence_u8_host")
+        return flows
 
     def inpaint_dev(self, img_d, cn, mask_d, out_d, w, h, radius, method, stream=None):
         st = lib().ofxcv_inpaint_u8(self.h, stream, img_d, w * cn, cn, mask_d, w, out_d, w * cn, w, h, float(radius), int(method))

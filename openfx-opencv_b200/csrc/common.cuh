@@ -14,6 +14,17 @@ struct ofxcv_buf {
     size_t cap = 0;
 };
 
+// one cached Farneback frame pyramid: the polynomial expansion R (5 coefficients per pixel) of a frame at every
+// scale, keyed by the caller's frame key so that frame t+1 of pair t is reused as frame t of pair t+1
+struct ofxcv_fb_pyr {
+    void* buf = nullptr;
+    size_t cap = 0;
+    uint64_t key = 0;    // 0 = anonymous (never matched)
+    uint64_t sig = 0;    // size + the parameters the pyramid depends on
+    uint64_t tick = 0;   // LRU
+    size_t off_q[16] = {0}, off_s[16] = {0};
+};
+
 struct ofxcv_timed_launch {
     cudaEvent_t a, b;
 };
@@ -42,6 +53,12 @@ struct ofxcv_ctx {
         cudaEvent_t a, b;
     };
     std::vector<prof_rec> prof;
+    ofxcv_fb_pyr fb_pyr[4];
+    uint64_t fb_tick = 0;
+    uint64_t fb_pyr_built = 0, fb_pyr_hits = 0;
+    // copy streams + events of the *_sequence_host entry points (created on first use)
+    cudaStream_t stream_up = nullptr, stream_down = nullptr;
+    cudaEvent_t seq_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int64_t inpaint_stats[4] = {0, 0, 0, 0};
     int64_t watershed_stats[4] = {0, 0, 0, 0};
 };

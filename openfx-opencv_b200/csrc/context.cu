@@ -130,6 +130,12 @@ void ofxcv_destroy(ofxcv_ctx* ctx)
         if (b.p) cudaFree(b.p);
     for (auto& b : ctx->pin)
         if (b.p) cudaFreeHost(b.p);
+    for (auto& y : ctx->fb_pyr)
+        if (y.buf) cudaFree(y.buf);
+    if (ctx->stream_up) cudaStreamDestroy(ctx->stream_up);
+    if (ctx->stream_down) cudaStreamDestroy(ctx->stream_down);
+    for (auto& e : ctx->seq_ev)
+        if (e) cudaEventDestroy(e);
     for (int f = 0; f < 3; f++)
         for (auto& t : ctx->timed[f]) {
             cudaEventDestroy(t.a);

@@ -169,6 +169,22 @@ __global__ void __launch_bounds__(256) cv_rgb_to_rgba_noise(const uint8_t* __res
     q[3] = 255;
 }
 
+// position-sensitive 64-bit content hash of a u8 plane: sum over pixels of splitmix64(value + golden * (index+1))
+__global__ void __launch_bounds__(256) cv_content_key(const uint8_t* __restrict__ img, ptrdiff_t stride, int W, int H,
+                                                      unsigned long long* __restrict__ acc)
+{
+    unsigned long long sum = 0;
+    const int y = blockIdx.y;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+        unsigned long long z = (unsigned long long)img[(size_t)y * stride + x] + 0x9E3779B97F4A7C15ull * ((unsigned long long)y * W + x + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        sum += z ^ (z >> 31);
+    }
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(acc, sum);
+}
+
 __global__ void __launch_bounds__(256) cv_seed_grid(int32_t* __restrict__ m, ptrdiff_t ms, int W, int H, int gx, int gy, int half)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,6 +317,25 @@ int ofxcv_rgb8_to_rgba8_noise(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t
     cv_rgb_to_rgba_noise<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, pick(ctx, stream)>>>(rgb, rgb_stride, mask, mask_stride, rgba, rgba_stride,
                                                                                        W, H, noise_div, seed);
     OFXCV_LAUNCH_CHECK(ctx);
+    return OFXCV_OK;
+}
+
+int ofxcv_content_key_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* img, ptrdiff_t stride, int W, int H, uint64_t* key)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!img || !key || W <= 0 || H <= 0 || stride < W) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    cudaStream_t s = pick(ctx, stream);
+    unsigned long long* acc = (unsigned long long*)ofxcv_ws(ctx, WS_MISC2, 8);
+    unsigned long long* host = (unsigned long long*)ofxcv_pin(ctx, 3, 8);
+    if (!acc || !host) return OFXCV_ERR_MEMORY;
+    OFXCV_CUDA(ctx, cudaMemsetAsync(acc, 0, 8, s));
+    cv_content_key<<<dim3(ofxcv_div_up(W, 1024) > 0 ? ofxcv_div_up(W, 1024) : 1, H), 256, 0, s>>>(img, stride, W, H, acc);
+    OFXCV_LAUNCH_CHECK(ctx);
+    OFXCV_CUDA(ctx, cudaMemcpyAsync(host, acc, 8, cudaMemcpyDeviceToHost, s));
+    OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+    uint64_t k = (uint64_t)*host ^ ((uint64_t)W << 40) ^ ((uint64_t)H << 20);
+    *key = k ? k : 1;
     return OFXCV_OK;
 }
 

@@ -205,6 +205,10 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
     float* out_dev = dev ? (float*)dst.img.pixel(win.x1, win.y1) : (float*)d_dst.p;
     const ptrdiff_t out_stride = dev ? dst.img.rowBytes : (ptrdiff_t)W * 16;
     stage_gray(ctx, ref.img, win, dev, stage, d_float, (uint8_t*)d_gray0.p);
+    // content keys: the pyramid of a gray frame is shared by the forward and the backward flow of this render and
+    // by the neighbouring renders of the clip (frame t+1 here is frame t of the next render)
+    uint64_t key0 = 0;
+    check_cv(ofxcv_content_key_u8(ctx, nullptr, (const uint8_t*)d_gray0.p, W, W, H, &key0));
     // channels set to "0" must read 0: scatter a zero flow into all four channels first
     check_cv(ofxcv_memset(ctx, nullptr, d_flow.p, 0, n * 8));
     {
@@ -216,8 +220,10 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
         if (gHost.effect->abort(effect)) return kOfxStatOK;
         ImageGuard other(gHost, d->src, dir == 0 ? a.time + 1 : a.time - 1);
         stage_gray(ctx, other.img, win, dev, stage, d_float, (uint8_t*)d_gray1.p);
-        check_cv(ofxcv_farneback_u8(ctx, nullptr, (const uint8_t*)d_gray0.p, (const uint8_t*)d_gray1.p, W, W, H, (float*)d_flow.p,
-                                    (ptrdiff_t)W * 8, &par));
+        uint64_t key1 = 0;
+        check_cv(ofxcv_content_key_u8(ctx, nullptr, (const uint8_t*)d_gray1.p, W, W, H, &key1));
+        check_cv(ofxcv_farneback_u8_keyed(ctx, nullptr, (const uint8_t*)d_gray0.p, (const uint8_t*)d_gray1.p, W, W, H, (float*)d_flow.p,
+                                          (ptrdiff_t)W * 8, &par, key0, key1));
         int sel[4];
         const int u = dir == 0 ? 1 : 3, v = dir == 0 ? 2 : 4;
         for (int c = 0; c < 4; c++) sel[c] = ch[c] == u ? 0 : ch[c] == v ? 1 : -1;

@@ -53,3 +53,70 @@ def test_farneback_params_and_errors(ctx, pkg, synth):
     got = ctx.farneback(prev, nxt, pkg.FbParams(poly_n=7, poly_sigma=1.5, levels=1, iterations=2))
     ref = oracle.farneback(prev, nxt, levels=1, iters=2, poly_n=7, poly_sigma=1.5)
     assert np.abs(got - ref).max(axis=2).mean() <= STRICT_MEAN
+
+
+def test_sequence_equals_pairwise_and_builds_each_pyramid_once(ctx, pkg, synth):
+    """ofxcv_farneback_sequence_u8[_host] must give the bits of the pair-by-pair call, and build each frame's pyramid once."""
+    h, w, n = 135, 240, 5
+    base = synth.gray(synth.texture(h, w, seed=11))
+    frames = [synth.shift_bilinear(base, 1.5 * f, -0.75 * f) for f in range(n)]
+    p = pkg.FbParams(levels=2, iterations=4)
+    ref = [ctx.farneback(frames[t], frames[t + 1], p) for t in range(n - 1)]
+    b0, h0 = ctx.farneback_cache_stats()
+    got = ctx.farneback_sequence(frames, p)
+    b1, h1 = ctx.farneback_cache_stats()
+    assert b1 - b0 == n                            # one pyramid per frame (the host pipeline hands them on directly)
+    for t in range(n - 1):
+        assert np.array_equal(got[t], ref[t]), "host sequence flow %d differs from the pairwise call" % t
+    # device-resident flavour
+    d_frames = ctx.to_device(np.stack(frames))
+    d_flows = ctx.alloc((n - 1) * w * h * 8)
+    ctx.farneback_sequence_dev(d_frames.ptr, w, h, n, d_flows.ptr, p)
+    dev = d_flows.download((n - 1, h, w, 2), np.float32)
+    b2, h2 = ctx.farneback_cache_stats()
+    assert b2 - b1 == n and h2 - h1 == n - 2       # n pyramids built, each interior frame found again once
+    for t in range(n - 1):
+        assert np.array_equal(dev[t], ref[t])
+    # pinned host buffers take the overlapped path: same bits
+    pf = [ctx.pinned_array((h, w), np.uint8) for _ in range(n)]
+    for a, b in zip(pf, frames):
+        a[...] = b
+    po = [ctx.pinned_array((h, w, 2), np.float32) for _ in range(n - 1)]
+    ctx.farneback_sequence(pf, p, out=po)
+    for t in range(n - 1):
+        assert np.array_equal(po[t], ref[t])
+
+
+def test_keyed_forward_backward_shares_pyramids(ctx, pkg, synth):
+    """A default VectorGenerator render needs t->t+1 and t->t-1: with keys, frame t is expanded once."""
+    h, w = 96, 128
+    base = synth.gray(synth.texture(h, w, seed=12))
+    f = [synth.shift_bilinear(base, 2.0 * i, 1.0 * i) for i in range(3)]
+    d = [ctx.to_device(x) for x in f]
+    out_f, out_b = ctx.alloc(w * h * 8), ctx.alloc(w * h * 8)
+    p = pkg.FbParams(levels=1, iterations=3)
+    ref_f, ref_b = ctx.farneback(f[1], f[2], p), ctx.farneback(f[1], f[0], p)
+    b0, h0 = ctx.farneback_cache_stats()
+    ctx.farneback_keyed_dev(d[1].ptr, d[2].ptr, w, h, out_f.ptr, 1001, 1002, p)
+    ctx.farneback_keyed_dev(d[1].ptr, d[0].ptr, w, h, out_b.ptr, 1001, 1000, p)
+    ctx.synchronize()
+    b1, h1 = ctx.farneback_cache_stats()
+    assert (b1 - b0, h1 - h0) == (3, 1)
+    assert np.array_equal(out_f.download((h, w, 2), np.float32), ref_f)
+    assert np.array_equal(out_b.download((h, w, 2), np.float32), ref_b)
+    # a different size under the same key must not hit
+    small = synth.gray(synth.texture(64, 80, seed=13))
+    ctx.farneback_keyed_dev(ctx.to_device(small).ptr, ctx.to_device(small).ptr, 80, 64, ctx.alloc(80 * 64 * 8).ptr, 1001, 1002, p)
+    ctx.synchronize()
+    b2, h2 = ctx.farneback_cache_stats()
+    assert b2 - b1 == 2 and h2 == h1
+
+
+def test_content_key(ctx, synth):
+    a = synth.gray(synth.texture(64, 80, seed=21))
+    b = a.copy()
+    b[10, 10] ^= 1
+    c = np.ascontiguousarray(a[:, ::-1])          # same histogram, different positions
+    ka, kb, kc = (ctx.content_key(ctx.to_device(x).ptr, 80, 64) for x in (a, b, c))
+    assert ka == ctx.content_key(ctx.to_device(a.copy()).ptr, 80, 64)
+    assert len({ka, kb, kc}) == 3 and 0 not in (ka, kb, kc)
