@@ -237,10 +237,20 @@ def run_ours(args):
     ms = timed(step_resident, args.steps)
     ctx.timing(False)
     launches = ctx.launch_count() - l0
-    n_iter, iter_ms = ctx.kernel_time_ms(0)
+    n_iter_situ, iter_ms_situ = ctx.kernel_time_ms(0)   # with the other lane's kernels sharing the GPU
     clocks = sampler.stop() if sampler else None
     # the same K steps without the per-kernel events, to show what the instrumentation costs
     ms_plain = timed(step_resident, args.steps)
+    # the dominant kernel on its own: the same steps with ONE pair in flight, so that no other kernel shares the SMs
+    ctx.farneback_set_lanes(1)
+    step_resident()
+    ctx.synchronize()
+    ctx.kernel_time_ms(0)
+    ctx.timing(True)
+    ms_one_lane = timed(step_resident, args.steps)
+    ctx.timing(False)
+    n_iter, iter_ms = ctx.kernel_time_ms(0)
+    ctx.farneback_set_lanes(2)
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -270,6 +280,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "fb_band3<ITER> at %dx%d (full-resolution Farneback iteration launches)" % (W, H), "launches": n_iter,
                          "us_per_launch": 1e3 * iter_ms / max(n_iter, 1), "algorithmic_bytes_per_launch": launch_bytes,
+                         "timed": "CUDA events around every such launch over %d steps with one pair in flight (%.1f frames/s in that pass); "
+                                  "in the headline pass two pairs are in flight and the same launches share the SMs with the other "
+                                  "pair's kernels: %.1f us per launch in situ" % (
+                                      args.steps, world * count * args.steps / (ms_one_lane * 1e-3), 1e3 * iter_ms_situ / max(n_iter_situ, 1)),
+                         "in_situ_us_per_launch": 1e3 * iter_ms_situ / max(n_iter_situ, 1),
                          "traffic_source": traffic_src, "peak_source": peak_src,
                          "whole_pair_effective_gbs": alg * pairs / world / (ms * 1e-3) / 1e9,
                          "whole_pair_frac": alg * pairs / world / (ms * 1e-3) / 1e9 / peak},

@@ -94,6 +94,7 @@ def lib():
         "ofxcv_farneback_u8_host": (i, [vp, vp, vp, pd, i, i, vp, pd, fbp]),
         "ofxcv_farneback_u8_keyed": (i, [vp, vp, vp, vp, pd, i, i, vp, pd, fbp, C.c_uint64, C.c_uint64]),
         "ofxcv_content_key_u8": (i, [vp, vp, vp, pd, i, i, C.POINTER(C.c_uint64)]),
+        "ofxcv_farneback_set_lanes": (None, [vp, i]),
         "ofxcv_farneback_cache_clear": (None, [vp]),
         "ofxcv_farneback_cache_stats": (i, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "ofxcv_farneback_sequence_u8": (i, [vp, vp, vp, pd, sz, i, i, i, vp, pd, sz, fbp]),
@@ -332,6 +333,9 @@ class Context:
         params = params or FbParams()
         st = lib().ofxcv_farneback_u8_keyed(self.h, stream, prev_d, next_d, w, w, h, flow_d, w * 8, C.byref(params), key_prev, key_next)
         self._check(st, "ofxcv_farneback_u8_keyed")
+
+    def farneback_set_lanes(self, lanes):
+        lib().ofxcv_farneback_set_lanes(self.h, int(lanes))
 
     def content_key(self, img_d, w, h):
         k = C.c_uint64(0)

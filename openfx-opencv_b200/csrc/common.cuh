@@ -23,6 +23,9 @@ struct ofxcv_fb_pyr {
     uint64_t sig = 0;    // size + the parameters the pyramid depends on
     uint64_t tick = 0;   // LRU
     size_t off_q[16] = {0}, off_s[16] = {0};
+    cudaEvent_t built = nullptr;  // recorded on the build stream after the pyramid is complete
+    cudaEvent_t used[2] = {nullptr, nullptr};  // recorded on a solve lane's stream after a solve that read it
+    bool used_pending[2] = {false, false};
 };
 
 struct ofxcv_timed_launch {
@@ -36,7 +39,7 @@ struct ofxcv_ctx {
     std::string last_error;
     uint64_t launches = 0;
     // named device workspaces, grown on demand, reused between calls
-    ofxcv_buf ws[32];
+    ofxcv_buf ws[48];
     // pinned host staging for the *_host entry points
     ofxcv_buf pin[4];
     // per-family kernel timing (bench.py roofline numerator): events recorded on the launching stream
@@ -56,8 +59,10 @@ struct ofxcv_ctx {
     ofxcv_fb_pyr fb_pyr[4];
     uint64_t fb_tick = 0;
     uint64_t fb_pyr_built = 0, fb_pyr_hits = 0;
+    int fb_lanes = 2;  // pairs in flight in ofxcv_farneback_sequence_u8 (ofxcv_farneback_set_lanes)
     // copy streams + events of the *_sequence_host entry points (created on first use)
-    cudaStream_t stream_up = nullptr, stream_down = nullptr;
+    cudaStream_t stream_up = nullptr, stream_down = nullptr, stream_lane[2] = {nullptr, nullptr};
+    cudaEvent_t lane_done[2] = {nullptr, nullptr}, lane_start = nullptr;
     cudaEvent_t seq_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int64_t inpaint_stats[4] = {0, 0, 0, 0};
     int64_t watershed_stats[4] = {0, 0, 0, 0};
@@ -168,6 +173,13 @@ enum {
     WS_FB_SINT,  // per-band interior difference sums of the running column sum
     WS_FB_TOT,   // per-band totals / exclusive prefixes (ping-pong)
     WS_FB_CNT,   // per-strip finish tickets of the band kernel
+    WS_FB1_MAQ,  // second solve lane of the Farneback sequence entry points (two pairs in flight)
+    WS_FB1_MAS,
+    WS_FB1_MBQ,
+    WS_FB1_MBS,
+    WS_FB1_FLOWA,
+    WS_FB1_FLOWB,
+    WS_FB1_TOT,
     WS_COUNT
 };
-static_assert(WS_COUNT <= 32, "workspace slots");
+static_assert(WS_COUNT <= 48, "workspace slots");

@@ -130,8 +130,17 @@ void ofxcv_destroy(ofxcv_ctx* ctx)
         if (b.p) cudaFree(b.p);
     for (auto& b : ctx->pin)
         if (b.p) cudaFreeHost(b.p);
-    for (auto& y : ctx->fb_pyr)
+    for (auto& y : ctx->fb_pyr) {
         if (y.buf) cudaFree(y.buf);
+        if (y.built) cudaEventDestroy(y.built);
+        for (auto& e : y.used)
+            if (e) cudaEventDestroy(e);
+    }
+    for (auto& st : ctx->stream_lane)
+        if (st) cudaStreamDestroy(st);
+    for (auto& e : ctx->lane_done)
+        if (e) cudaEventDestroy(e);
+    if (ctx->lane_start) cudaEventDestroy(ctx->lane_start);
     if (ctx->stream_up) cudaStreamDestroy(ctx->stream_up);
     if (ctx->stream_down) cudaStreamDestroy(ctx->stream_down);
     for (auto& e : ctx->seq_ev)
