@@ -357,10 +357,14 @@ class Context:
         """frames: list of HxW uint8 host arrays (page-locked ones overlap copies with compute).  Returns the list of
         len(frames)-1 HxWx2 float32 flow fields (written into `out` when given)."""
         params = params or FbParams()
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]   # no copy for C-ordered (e.g. page-locked) arrays
         h, w = frames[0].shape
         n = len(frames)
+        if any(f.shape != (h, w) for f in frames):
+            raise ValueError("all frames must be HxW uint8 of one size")
         flows = out if out is not None else [np.empty((h, w, 2), np.float32) for _ in range(n - 1)]
         fp = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        assert all(f.shape == (h, w, 2) and f.dtype == np.float32 and f.flags.c_contiguous for f in flows)
         op = (C.c_void_p * (n - 1))(*[f.ctypes.data for f in flows])
         st = lib().ofxcv_farneback_sequence_u8_host(self.h, fp, w, w, h, n, op, w * 8, C.byref(params))
         self._check(st, "ofxcv_farneback_sequence_u8_host")

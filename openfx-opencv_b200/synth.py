@@ -35,7 +35,7 @@ def shift_bilinear(img, dx, dy):
     top = f[y0c][:, x0c] * (1 - fx) + f[y0c][:, x1c] * fx
     bot = f[y1c][:, x0c] * (1 - fx) + f[y1c][:, x1c] * fx
     out = top * (1 - fy)[:, None] + bot * fy[:, None]
-    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(out), 0, 255).astype(np.uint8))
 
 
 def flow_pair(h, w, seed=3, dx=2.5, dy=-1.5):
