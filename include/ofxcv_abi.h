@@ -189,6 +189,19 @@ OFXCV_API int ofxcv_watershed_last_stats(const ofxcv_ctx* ctx, int64_t stats[4])
 OFXCV_API int ofxcv_rgba32f_to_srgb_gray8(ofxcv_ctx* ctx, ofxcv_stream stream, const float* src,
                                           ptrdiff_t src_stride, int ncomp, uint8_t* dst, ptrdiff_t dst_stride,
                                           int W, int H);
+/* float (linear) -> 8-bit sRGB, packed: GenericOpenCVPlugin::fetchCVImage8U
+ * (/root/reference/OpenCV/GenericOpenCVPlugin.cpp:177-221) = Lut::to_byte_packed_nodither
+ * (/root/reference/SupportExt/ofxsLut.h:389-444) over WHOLE rows.  src/dst component counts
+ * 1 (alpha), 3 or 4; colour through the sRGB table, alpha through floatToInt<256>; a 3-component source gives alpha 0.
+ * Strides in bytes (src_stride may be negative). */
+OFXCV_API int ofxcv_rgba32f_to_srgb8_packed(ofxcv_ctx* ctx, ofxcv_stream stream, const float* src, ptrdiff_t src_stride,
+                                            int src_ncomp, uint8_t* dst, ptrdiff_t dst_stride, int dst_ncomp, int W,
+                                            int H);
+/* 8-bit sRGB -> float (linear), packed: GenericOpenCVPlugin::cvImageToOfxImage (GenericOpenCVPlugin.cpp:267-325) =
+ * Lut::from_byte_packed (ofxsLut.h:536-581).  Same component count on both sides (1, 3 or 4). */
+OFXCV_API int ofxcv_srgb8_packed_to_rgba32f(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* src,
+                                            ptrdiff_t src_stride, float* dst, ptrdiff_t dst_stride, int ncomp, int W,
+                                            int H);
 /* flow -> selected RGBA channels with the renderScale division: VectorGenerator.cpp:494-519.
  * chan_sel[c] for c = R,G,B,A: -1 = leave untouched, 0 = flow.x / scale_x, 1 = flow.y / scale_y. */
 OFXCV_API int ofxcv_flow_to_rgba32f(ofxcv_ctx* ctx, ofxcv_stream stream, const float* flow, ptrdiff_t flow_stride,

@@ -110,6 +110,8 @@ def lib():
         "ofxcv_watershed_workspace_bytes": (sz, [i, i, i]),
         "ofxcv_watershed_last_stats": (i, [vp, C.POINTER(C.c_int64)]),
         "ofxcv_rgba32f_to_srgb_gray8": (i, [vp, vp, vp, pd, i, vp, pd, i, i]),
+        "ofxcv_rgba32f_to_srgb8_packed": (i, [vp, vp, vp, pd, i, vp, pd, i, i, i]),
+        "ofxcv_srgb8_packed_to_rgba32f": (i, [vp, vp, vp, pd, vp, pd, i, i, i]),
         "ofxcv_flow_to_rgba32f": (i, [vp, vp, vp, pd, vp, pd, i, i, C.POINTER(C.c_int), d, d]),
         "ofxcv_rgba8_to_rgb8_mask": (i, [vp, vp, vp, pd, vp, pd, vp, pd, i, i, i]),
         "ofxcv_rgb8_to_rgba8": (i, [vp, vp, vp, pd, vp, pd, i, i]),
@@ -387,6 +389,22 @@ class Context:
         dst = self.alloc(w * h)
         self._check(lib().ofxcv_rgba32f_to_srgb_gray8(self.h, None, src.ptr, w * nc * 4, nc, dst.ptr, w, w, h), "ofxcv_rgba32f_to_srgb_gray8")
         return dst.download((h, w), np.uint8)
+
+    def rgba32f_to_srgb8_packed(self, img, dst_ncomp):
+        img = np.ascontiguousarray(img, np.float32)
+        h, w = img.shape[:2]
+        sn = 1 if img.ndim == 2 else img.shape[2]
+        src, dst = self.to_device(img), self.alloc(w * h * dst_ncomp)
+        self._check(lib().ofxcv_rgba32f_to_srgb8_packed(self.h, None, src.ptr, w * sn * 4, sn, dst.ptr, w * dst_ncomp, dst_ncomp, w, h),
+                    "ofxcv_rgba32f_to_srgb8_packed")
+        return dst.download((h, w, dst_ncomp), np.uint8)
+
+    def srgb8_packed_to_rgba32f(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, n = img.shape
+        src, dst = self.to_device(img), self.alloc(w * h * n * 4)
+        self._check(lib().ofxcv_srgb8_packed_to_rgba32f(self.h, None, src.ptr, w * n, dst.ptr, w * n * 4, n, w, h), "ofxcv_srgb8_packed_to_rgba32f")
+        return dst.download((h, w, n), np.float32)
 
     def flow_to_rgba32f(self, flow, dst, chan_sel, scale_x=1.0, scale_y=1.0):
         flow = np.ascontiguousarray(flow, np.float32)

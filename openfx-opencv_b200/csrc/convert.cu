@@ -40,6 +40,7 @@ int float_to_ff01(float value)
 
 std::once_flag g_lut_once;
 uint16_t g_lut[0x10000];
+float g_from_lut[256];  // byte -> linear float (Lut::fromFunc_uint8_to_float, ofxsLut.h:183-189)
 
 void build_lut()
 {
@@ -49,7 +50,16 @@ void build_lut()
         uint32_t bits;
         memcpy(&bits, &f, 4);
         g_lut[bits >> 16] = (uint16_t)(b << 8);
+        g_from_lut[b] = f;
     }
+}
+
+// floatToInt<256> of the reference (ofxsLut.h:57-68): float product, double +0.5, truncation
+__device__ __forceinline__ uint8_t alpha_to_byte(float v)
+{
+    if (v <= 0.f) return 0;
+    if (v >= 1.f) return 255;
+    return (uint8_t)(int)((double)(v * 255.f) + 0.5);
 }
 
 __global__ void __launch_bounds__(256) cv_luma_srgb8(const char* __restrict__ src, ptrdiff_t src_stride, int ncomp,
@@ -72,6 +82,47 @@ __global__ void __launch_bounds__(256) cv_luma_srgb8(const char* __restrict__ sr
     }
     unsigned hi = __float_as_uint(l) >> 16;
     dst[(size_t)y * dst_stride + x] = (uint8_t)((lut[hi] + 0x80) >> 8);
+}
+
+// Lut::to_byte_packed_nodither (ofxsLut.h:389-444) over whole rows: colour channels through the hipart table,
+// alpha through floatToInt<256>; a 3-component source leaves alpha 0, a 1-component source is alpha only
+__global__ void __launch_bounds__(256) cv_to_byte_packed(const char* __restrict__ src, ptrdiff_t src_stride, int sn,
+                                                         uint8_t* __restrict__ dst, ptrdiff_t dst_stride, int dn, int W, int H,
+                                                         const uint16_t* __restrict__ lut)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const float* p = (const float*)(src + (ptrdiff_t)y * src_stride) + (size_t)x * sn;
+    uint8_t t[4] = {0, 0, 0, 0};
+    if (sn == 1) t[3] = alpha_to_byte(p[0]);
+    else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) t[k] = (uint8_t)((lut[__float_as_uint(p[k]) >> 16] + 0x80) >> 8);
+        if (sn == 4) t[3] = alpha_to_byte(p[3]);
+    }
+    uint8_t* q = dst + (size_t)y * dst_stride + (size_t)x * dn;
+    if (dn == 1) q[0] = t[3];
+    else
+        for (int k = 0; k < dn; k++) q[k] = t[k];
+}
+
+// Lut::from_byte_packed (ofxsLut.h:536-581): colour bytes through the 256-entry table, alpha = b / 255.f
+__global__ void __launch_bounds__(256) cv_from_byte_packed(const uint8_t* __restrict__ src, ptrdiff_t src_stride,
+                                                           char* __restrict__ dst, ptrdiff_t dst_stride, int n, int W, int H,
+                                                           const float* __restrict__ from)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const uint8_t* p = src + (size_t)y * src_stride + (size_t)x * n;
+    float* q = (float*)(dst + (ptrdiff_t)y * dst_stride) + (size_t)x * n;
+    if (n == 1) q[0] = (float)p[0] / 255.f;
+    else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) q[k] = from[p[k]];
+        if (n == 4) q[3] = (float)p[3] / 255.f;
+    }
 }
 
 __global__ void __launch_bounds__(256) cv_flow_to_rgba(const char* __restrict__ flow, ptrdiff_t flow_stride,
@@ -243,6 +294,22 @@ extern "C" {
 
 static cudaStream_t pick(ofxcv_ctx* ctx, ofxcv_stream s) { return s ? (cudaStream_t)s : ctx->stream; }
 
+// device copies of the two sRGB tables, uploaded once per context: [65536 x u16 hipart table | 256 x f32 from-table]
+static int srgb_tables(ofxcv_ctx* ctx, cudaStream_t s, const uint16_t** to, const float** from)
+{
+    std::call_once(g_lut_once, build_lut);
+    char* dl = (char*)ctx->ws[WS_LUT].p;
+    if (!dl) {
+        dl = (char*)ofxcv_ws(ctx, WS_LUT, sizeof(g_lut) + sizeof(g_from_lut));
+        if (!dl) return OFXCV_ERR_MEMORY;
+        OFXCV_CUDA(ctx, cudaMemcpyAsync(dl, g_lut, sizeof(g_lut), cudaMemcpyHostToDevice, s));
+        OFXCV_CUDA(ctx, cudaMemcpyAsync(dl + sizeof(g_lut), g_from_lut, sizeof(g_from_lut), cudaMemcpyHostToDevice, s));
+    }
+    *to = (const uint16_t*)dl;
+    *from = (const float*)(dl + sizeof(g_lut));
+    return OFXCV_OK;
+}
+
 int ofxcv_rgba32f_to_srgb_gray8(ofxcv_ctx* ctx, ofxcv_stream stream, const float* src, ptrdiff_t src_stride, int ncomp,
                                 uint8_t* dst, ptrdiff_t dst_stride, int W, int H)
 {
@@ -251,14 +318,46 @@ int ofxcv_rgba32f_to_srgb_gray8(ofxcv_ctx* ctx, ofxcv_stream stream, const float
     if (ncomp == 4 && (((uintptr_t)src | (size_t)(src_stride < 0 ? -src_stride : src_stride)) & 15)) return OFXCV_ERR_BAD_ARG;
     ofxcv_device_guard guard(ctx->device);
     cudaStream_t s = pick(ctx, stream);
-    std::call_once(g_lut_once, build_lut);
-    uint16_t* dl = (uint16_t*)ctx->ws[WS_LUT].p;
-    if (!dl) {
-        dl = (uint16_t*)ofxcv_ws(ctx, WS_LUT, sizeof(g_lut));
-        if (!dl) return OFXCV_ERR_MEMORY;
-        OFXCV_CUDA(ctx, cudaMemcpyAsync(dl, g_lut, sizeof(g_lut), cudaMemcpyHostToDevice, s));
-    }
+    const uint16_t* dl;
+    const float* from;
+    int st = srgb_tables(ctx, s, &dl, &from);
+    if (st < 0) return st;
     cv_luma_srgb8<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>((const char*)src, src_stride, ncomp, dst, dst_stride, W, H, dl);
+    OFXCV_LAUNCH_CHECK(ctx);
+    return OFXCV_OK;
+}
+
+int ofxcv_rgba32f_to_srgb8_packed(ofxcv_ctx* ctx, ofxcv_stream stream, const float* src, ptrdiff_t src_stride, int src_ncomp,
+                                  uint8_t* dst, ptrdiff_t dst_stride, int dst_ncomp, int W, int H)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    auto okn = [](int n) { return n == 1 || n == 3 || n == 4; };
+    if (!src || !dst || W <= 0 || H <= 0 || !okn(src_ncomp) || !okn(dst_ncomp) || dst_stride < (ptrdiff_t)W * dst_ncomp || (src_stride & 3))
+        return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    cudaStream_t s = pick(ctx, stream);
+    const uint16_t* to;
+    const float* from;
+    int st = srgb_tables(ctx, s, &to, &from);
+    if (st < 0) return st;
+    cv_to_byte_packed<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>((const char*)src, src_stride, src_ncomp, dst, dst_stride, dst_ncomp, W, H, to);
+    OFXCV_LAUNCH_CHECK(ctx);
+    return OFXCV_OK;
+}
+
+int ofxcv_srgb8_packed_to_rgba32f(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* src, ptrdiff_t src_stride, float* dst,
+                                  ptrdiff_t dst_stride, int ncomp, int W, int H)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!src || !dst || W <= 0 || H <= 0 || (ncomp != 1 && ncomp != 3 && ncomp != 4) || src_stride < (ptrdiff_t)W * ncomp || (dst_stride & 3))
+        return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    cudaStream_t s = pick(ctx, stream);
+    const uint16_t* to;
+    const float* from;
+    int st = srgb_tables(ctx, s, &to, &from);
+    if (st < 0) return st;
+    cv_from_byte_packed<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>(src, src_stride, (char*)dst, dst_stride, ncomp, W, H, from);
     OFXCV_LAUNCH_CHECK(ctx);
     return OFXCV_OK;
 }

@@ -140,6 +140,25 @@ def srgb_from_byte_table():
     return srgb_tables()[1]
 
 
+def to_byte_packed(img, dst_ncomp):
+    """Lut::to_byte_packed_nodither over whole rows: float (h,w[,n]) -> uint8 (h,w[,dst_ncomp])."""
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape[:2]
+    sn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty((h, w, dst_ncomp), np.uint8)
+    lib().orc_to_byte_packed(_p(img), C.c_int(sn), _p(out), C.c_int(dst_ncomp), C.c_int(w), C.c_int(h))
+    return out
+
+
+def from_byte_packed(img):
+    """Lut::from_byte_packed: uint8 (h,w,n) -> float32 (h,w,n)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, n = img.shape
+    out = np.empty((h, w, n), np.float32)
+    lib().orc_from_byte_packed(_p(img), _p(out), C.c_int(n), C.c_int(w), C.c_int(h))
+    return out
+
+
 def luma_srgb_gray8(img):
     img = np.ascontiguousarray(img, np.float32)
     h, w = img.shape[:2]

@@ -73,3 +73,49 @@ void orc_luma_srgb_gray8(const float* src, int ncomp, uint8_t* dst, int w, int h
         dst[p] = (uint8_t)((to_table[orc_hipart(l)] + 0x80) >> 8);
     }
 }
+
+/* ---- packed conversions: Lut::to_byte_packed_nodither (ofxsLut.h:389-444), Lut::from_byte_packed (:536-581),
+ * floatToInt<256> / intToFloat<256> (:47-68), over whole rows ------------------------------------------------ */
+static uint8_t orc_alpha_to_byte(float v)
+{
+    if (v <= 0) return 0;
+    if (v >= 1.) return 255;
+    return (uint8_t)(int)(v * 255 + 0.5);
+}
+
+void orc_to_byte_packed(const float* src, int sn, uint8_t* dst, int dn, int w, int h)
+{
+    static uint16_t to_table[0x10000];
+    static float from_table[256];
+    static int init = 0;
+    if (!init) { orc_srgb_tables(to_table, from_table); init = 1; }
+    for (long p = 0; p < (long)w * h; p++) {
+        const float* s = src + p * sn;
+        uint8_t t[4] = {0, 0, 0, 0};
+        if (sn == 1) t[3] = orc_alpha_to_byte(s[0]);
+        else {
+            for (int k = 0; k < 3; k++) t[k] = (uint8_t)((to_table[orc_hipart(s[k])] + 0x80) >> 8);
+            if (sn == 4) t[3] = orc_alpha_to_byte(s[3]);
+        }
+        uint8_t* d = dst + p * dn;
+        if (dn == 1) d[0] = t[3];
+        else for (int k = 0; k < dn; k++) d[k] = t[k];
+    }
+}
+
+void orc_from_byte_packed(const uint8_t* src, float* dst, int n, int w, int h)
+{
+    static uint16_t to_table[0x10000];
+    static float from_table[256];
+    static int init = 0;
+    if (!init) { orc_srgb_tables(to_table, from_table); init = 1; }
+    for (long p = 0; p < (long)w * h; p++) {
+        const uint8_t* s = src + p * n;
+        float* d = dst + p * n;
+        if (n == 1) d[0] = s[0] / (float)255;
+        else {
+            for (int k = 0; k < 3; k++) d[k] = from_table[s[k]];
+            if (n == 4) d[3] = s[3] / (float)255;
+        }
+    }
+}

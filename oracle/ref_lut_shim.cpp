@@ -20,4 +20,7 @@ unsigned char ref_luma_to_byte(float r, float g, float b)
     float l = 0.2126 * r + 0.7152 * g + 0.0722 * b;
     return g_manager.sRGBLut()->toColorSpaceUint8FromLinearFloatFast(l);
 }
+// alpha channel quantisers of the packed conversions (ofxsLut.h:47-68)
+unsigned char ref_alpha_to_byte(float a) { return (unsigned char)OFX::Color::floatToInt<256>(a); }
+float ref_alpha_from_byte(unsigned char b) { return OFX::Color::intToFloat<256>(b); }
 }

@@ -81,7 +81,16 @@ def lut():
     rng = np.random.default_rng(0)
     rgb = (rng.random((4096, 3), dtype=np.float32) * 1.2 - 0.1).astype(np.float32)
     luma = np.array([L.ref_luma_to_byte(*[C.c_float(v) for v in p]) for p in rgb], np.uint8)
-    np.savez_compressed(os.path.join(HERE, "lut_srgb_ref.npz"), to_byte_by_hipart=to, from_byte=fr, luma_rgb=rgb, luma_byte=luma)
+    # alpha quantisers of the packed conversions (floatToInt<256> / intToFloat<256>): dense sweep incl. the rounding ties
+    L.ref_alpha_to_byte.restype = C.c_ubyte; L.ref_alpha_to_byte.argtypes = [C.c_float]
+    L.ref_alpha_from_byte.restype = C.c_float; L.ref_alpha_from_byte.argtypes = [C.c_ubyte]
+    alpha_in = np.concatenate([np.linspace(-0.25, 1.25, 6001, dtype=np.float32),
+                               ((np.arange(256, dtype=np.float32) + 0.5) / 255).astype(np.float32),
+                               np.nextafter(((np.arange(256, dtype=np.float32) + 0.5) / 255).astype(np.float32), np.float32(0))])
+    alpha_byte = np.array([L.ref_alpha_to_byte(C.c_float(v)) for v in alpha_in], np.uint8)
+    alpha_from = np.array([L.ref_alpha_from_byte(b) for b in range(256)], np.float32)
+    np.savez_compressed(os.path.join(HERE, "lut_srgb_ref.npz"), to_byte_by_hipart=to, from_byte=fr, luma_rgb=rgb, luma_byte=luma,
+                        alpha_in=alpha_in, alpha_byte=alpha_byte, alpha_from=alpha_from)
 
 
 if __name__ == "__main__":

@@ -74,3 +74,25 @@ def test_rgb_to_rgba_and_seed_grid_and_paint(ctx, oracle, synth):
         mean = np.floor(rgb[sel].astype(np.float64).mean(axis=0) + 0.5 + 1e-9)
         assert np.abs(vis[sel][0, :3].astype(int) - mean).max() <= 1
     assert (vis[lab == -1][:, :3] == 0).all()
+
+
+def test_packed_srgb_conversions(ctx, oracle):
+    """ofxcv_rgba32f_to_srgb8_packed / ofxcv_srgb8_packed_to_rgba32f against the oracle (itself pinned to the reference's
+    compiled ofxsLut code): every component-count combination, out-of-range values, all 256 codes round trip."""
+    rng = np.random.default_rng(3)
+    img = (rng.random((29, 41, 4), dtype=np.float32) * 1.3 - 0.15).astype(np.float32)
+    img[0, 0] = [0, 1, np.inf, 0.5]; img[0, 1] = [np.nan, -np.inf, 1e-8, 1.0]; img[0, 2] = [0.0031308, 0.04045, 0.5, 0.0019607844]
+    for sn in (4, 3, 1):
+        src = img[..., 0].copy() if sn == 1 else np.ascontiguousarray(img[..., :sn])
+        for dn in (4, 3, 1):
+            got = ctx.rgba32f_to_srgb8_packed(src, dn)
+            assert np.array_equal(got, oracle.to_byte_packed(src, dn)), (sn, dn)
+    codes = rng.integers(0, 256, (17, 23, 4), dtype=np.uint8)
+    codes[0, :, :] = np.arange(23)[:, None] * 11
+    for n in (4, 3, 1):
+        src = np.ascontiguousarray(codes[..., :n])
+        got = ctx.srgb8_packed_to_rgba32f(src)
+        assert np.array_equal(got, oracle.from_byte_packed(src)), n
+    b = np.arange(256, dtype=np.uint8)
+    lin = ctx.srgb8_packed_to_rgba32f(np.stack([b, b, b, b], axis=-1).reshape(1, 256, 4))
+    assert np.array_equal(ctx.rgba32f_to_srgb8_packed(lin, 4)[0], np.stack([b, b, b, b], axis=-1))

@@ -74,3 +74,31 @@ def test_oracle_lut_vs_compiled_reference(oracle):
     ref = np.array([L.ref_luma_to_byte(*[C.c_float(v) for v in p]) for p in rgb], np.uint8)
     got = oracle.luma_srgb_gray8(rgb.reshape(40, 50, 3)).ravel()
     assert np.array_equal(got, ref)
+
+
+def test_packed_conversions_match_reference_tables(oracle):
+    """oracle to_byte_packed / from_byte_packed against values produced by the reference's own compiled ofxsLut code
+    (tests/golden/lut_srgb_ref.npz: hipart table, from-byte table, floatToInt<256> / intToFloat<256> sweeps)."""
+    z = np.load(os.path.join(G, "lut_srgb_ref.npz"))
+    # colour channels: every hipart code once (mid-bucket float), through a 3-component image
+    codes = np.arange(0x10000, dtype=np.uint32)
+    f = ((codes << 16) | 0x8000).view(np.float32)
+    img = np.stack([f, f, f], axis=-1).reshape(256, 256, 3)
+    got = oracle.to_byte_packed(img, 3)
+    assert np.array_equal(got[..., 0].ravel(), z["to_byte_by_hipart"]) and np.array_equal(got[..., 2].ravel(), z["to_byte_by_hipart"])
+    # alpha: the dense sweep incl. rounding ties, as a 1-component image and as channel 3 of RGBA
+    a = z["alpha_in"]
+    assert np.array_equal(oracle.to_byte_packed(a.reshape(1, -1), 1)[0, :, 0], z["alpha_byte"])
+    rgba = np.zeros((1, a.size, 4), np.float32); rgba[0, :, 3] = a
+    out = oracle.to_byte_packed(rgba, 4)
+    assert np.array_equal(out[0, :, 3], z["alpha_byte"]) and not out[..., :3].any()
+    # RGB source -> RGBA destination leaves alpha 0; RGBA -> alpha-only keeps alpha
+    assert not oracle.to_byte_packed(img, 4)[..., 3].any()
+    assert np.array_equal(oracle.to_byte_packed(rgba, 1)[0, :, 0], z["alpha_byte"])
+    # from_byte_packed: all 256 codes
+    b = np.arange(256, dtype=np.uint8)
+    back = oracle.from_byte_packed(np.stack([b, b, b, b], axis=-1).reshape(1, 256, 4))
+    assert np.array_equal(back[0, :, 0], z["from_byte"]) and np.array_equal(back[0, :, 3], z["alpha_from"])
+    assert np.array_equal(oracle.from_byte_packed(b.reshape(1, 256, 1))[0, :, 0], z["alpha_from"])
+    # every 8-bit colour code survives the round trip (the reference patches its table for exactly this)
+    assert np.array_equal(oracle.to_byte_packed(back, 4)[0, :, :3], np.stack([b, b, b], axis=-1))
