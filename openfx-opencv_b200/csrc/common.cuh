@@ -79,6 +79,7 @@ struct ofxcv_prof_scope {
     ofxcv_ctx* ctx;
     cudaStream_t s;
     bool on;
+    size_t idx = 0;  // scopes may nest
     ofxcv_prof_scope(ofxcv_ctx* c, cudaStream_t st, const char* name, int tag) : ctx(c), s(st), on(c->prof_on)
     {
         if (!on) return;
@@ -94,11 +95,12 @@ struct ofxcv_prof_scope {
             cudaEventCreate(&r.b);
         }
         cudaEventRecord(r.a, s);
+        idx = ctx->prof.size();
         ctx->prof.push_back(r);
     }
     ~ofxcv_prof_scope()
     {
-        if (on) cudaEventRecord(ctx->prof.back().b, s);
+        if (on) cudaEventRecord(ctx->prof[idx].b, s);
     }
 };
 

@@ -19,6 +19,7 @@
 //    the lanes evaluate the taps' weights in parallel, and the f32 accumulators are then summed in the CPU's
 //    row-major tap order (one lane per accumulator) so that every rounding matches.
 #include <math.h>
+#include <stdlib.h>
 
 #include <cub/cub.cuh>
 
@@ -443,6 +444,234 @@ ip_fill(const uint32_t* __restrict__ order, unsigned nfill, uint32_t cnt_base, c
     }
 }
 
+// ---- Stage B, second generation: the (2r+3)^2 neighbourhood of the pixel is staged in shared memory ----------------
+// ip_fill above issues ~1700 dependent L2 loads per pixel from inside the tap arithmetic (8 us per pixel), and the
+// fill order of an iid mask is a dependency chain thousands of pixels long (a pixel waits for every earlier-filled
+// hole pixel of its box), so the kernel runs at chain length x per-pixel latency.  Here a warp (a) loads hole/cnt of
+// the whole box in one round and spins only on the positions that are earlier-filled holes, (b) loads the colours
+// (+T for Telea) of the box in one more round into shared memory with the "known" flag packed beside them, (c)
+// evaluates the taps from shared memory only, and (d) sums the accumulators in tap order from registers.  Same
+// arithmetic, ~4x shorter per-pixel latency.  Used for radius <= IP2_MAXR (the plugin's range is [1, 10]).
+constexpr int IP2_MAXR = 10;
+
+template <int METHOD, int CN>
+__global__ void __launch_bounds__(IP_WARPS * 32)
+ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, uint32_t cnt_base, const uint8_t* __restrict__ hole,
+         const uint32_t* __restrict__ cnt, const float* __restrict__ t, uint8_t* out, ptrdiff_t ostride, uint8_t* done,
+         unsigned* __restrict__ ticket, int range, IpGeom g)
+{
+    constexpr int NACC = METHOD == OFXCV_INPAINT_TELEA ? 4 * CN : 2 * CN;
+    extern __shared__ __align__(16) unsigned char ip2_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ec = g.ec, er = g.er;
+    const int side = 2 * range + 1, ntaps = side * side;
+    const int bside = 2 * range + 3, nbox = bside * bside;
+    // per warp: packed colour+known word and T of every box position, then the term transpose buffer
+    const int nbox_pad = (nbox + 3) & ~3;
+    const size_t per_warp = (size_t)nbox_pad * 8 + 32 * (IP_MAXACC + 1) * 4;
+    uint32_t* s_px = reinterpret_cast<uint32_t*>(ip2_smem + per_warp * wid);
+    float* s_t = reinterpret_cast<float*>(s_px + nbox_pad);
+    float(*s_term)[IP_MAXACC + 1] = reinterpret_cast<float(*)[IP_MAXACC + 1]>(s_t + nbox_pad);
+    volatile uint8_t* vdone = done;
+
+    for (;;) {
+        unsigned tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1u);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk >= nfill) break;
+        const int id = (int)order[tk];
+        const uint32_t mycnt = cnt_base + tk;
+        const int i = id / ec, j = id - i * ec;
+        const int k0 = i - range - 1, l0 = j - range - 1;  // map coordinates of box position (0, 0)
+
+        // (a) hole / cnt of the box in one round; spin on the earlier-filled holes only
+        for (int b = lane; b < nbox; b += 32) {
+            const int bk = b / bside, bl = b - bk * bside;
+            const int k = k0 + bk, l = l0 + bl;
+            unsigned known = 1;
+            if (k >= 0 && l >= 0 && k < er && l < ec) {
+                const int n = k * ec + l;
+                if (hole[n]) {
+                    if (cnt[n] < mycnt) {
+                        while (vdone[n] == 0) { }
+                    } else {
+                        known = 0;
+                    }
+                }
+            }
+            s_px[b] = known << 24;
+        }
+        __syncwarp();
+        __threadfence();
+        // (b) colours (+T) of the box in one round
+        for (int b = lane; b < nbox; b += 32) {
+            const int bk = b / bside, bl = b - bk * bside;
+            const int k = k0 + bk, l = l0 + bl;
+            uint32_t px = s_px[b];
+            float tv = 0.f;
+            if (k >= 1 && l >= 1 && k <= g.H && l <= g.W) {
+                const uint8_t* o = out + (size_t)(k - 1) * ostride + (size_t)(l - 1) * CN;
+#pragma unroll
+                for (int c = 0; c < CN; c++) px |= (uint32_t)ld_u8_cg(o + c) << (8 * c);
+            }
+            if (METHOD == OFXCV_INPAINT_TELEA && k >= 0 && l >= 0 && k < er && l < ec) tv = t[k * ec + l];
+            s_px[b] = px;
+            s_t[b] = tv;
+        }
+        __syncwarp();
+
+        // box accessors: map position (k, l) / image position (r, c) = map (r+1, c+1)
+        auto bidx = [&](int k, int l) -> int { return (k - k0) * bside + (l - l0); };
+        auto known = [&](int k, int l) -> bool { return (s_px[bidx(k, l)] >> 24) != 0; };
+#define OUTP(r, c, ch) (int)((s_px[bidx((r) + 1, (c) + 1)] >> (8 * (ch))) & 0xffu)
+#define TV(k, l) s_t[bidx((k), (l))]
+
+        float gTx = 0.f, gTy = 0.f, ti = 0.f;
+        if (METHOD == OFXCV_INPAINT_TELEA) {
+            ti = TV(i, j);
+            if (known(i, j + 1)) {
+                if (known(i, j - 1)) gTx = (float)(TV(i, j + 1) - TV(i, j - 1)) * 0.5f;
+                else gTx = (float)(TV(i, j + 1) - ti);
+            } else {
+                if (known(i, j - 1)) gTx = (float)(ti - TV(i, j - 1));
+                else gTx = 0;
+            }
+            if (known(i + 1, j)) {
+                if (known(i - 1, j)) gTy = (float)(TV(i + 1, j) - TV(i - 1, j)) * 0.5f;
+                else gTy = (float)(TV(i + 1, j) - ti);
+            } else {
+                if (known(i - 1, j)) gTy = (float)(ti - TV(i - 1, j));
+                else gTy = 0;
+            }
+        }
+
+        float acc = 0.f;  // lane a < NACC owns accumulator a
+        if (METHOD == OFXCV_INPAINT_TELEA) { if ((lane & 3) == 3) acc = 1.0e-20f; }
+        else { if ((lane & 1) == 1) acc = 1.0e-20f; }
+
+        for (int base = 0; base < ntaps; base += 32) {
+            const int tp = base + lane;
+            bool valid = false;
+            float term[IP_MAXACC];
+#pragma unroll
+            for (int a = 0; a < IP_MAXACC; a++) term[a] = 0.f;
+            if (tp < ntaps) {
+                const int k = i - range + tp / side, l = j - range + tp % side;
+                if (k > 0 && l > 0 && k < er - 1 && l < ec - 1) {
+                    if (known(k, l) && (l - j) * (l - j) + (k - i) * (k - i) <= range * range) {
+                        valid = true;
+                        const int km = k - 1 + (k == 1), kp = k - 1 - (k == er - 2);
+                        const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ec - 2);
+                        const bool fr = known(k, l + 1), fl = known(k, l - 1), fd = known(k + 1, l), fu = known(k - 1, l);
+                        if (METHOD == OFXCV_INPAINT_TELEA) {
+                            float ry = (float)(i - k), rx = (float)(j - l);
+                            float vl = rx * rx + ry * ry;
+                            float dst = (float)(1. / (vl * sqrt((double)vl)));
+                            float lev = (float)(1. / (1 + (double)fabsf(TV(k, l) - ti)));  // f32 difference, f64 sum (C fabs)
+                            float dir = rx * gTx + ry * gTy;
+                            if (fabs(dir) <= 0.01) dir = 0.000001f;
+                            float w = (float)fabs(dst * lev * dir);
+#pragma unroll
+                            for (int c = 0; c < CN; c++) {
+                                float gIx, gIy;
+                                if (fr) {
+                                    if (fl) gIx = (float)(OUTP(km, lp + 1, c) - OUTP(km, lm - 1, c)) * 2.0f;
+                                    else gIx = (float)(OUTP(km, lp + 1, c) - OUTP(km, lm, c));
+                                } else {
+                                    if (fl) gIx = (float)(OUTP(km, lp, c) - OUTP(km, lm - 1, c));
+                                    else gIx = 0;
+                                }
+                                if (fd) {
+                                    if (fu) gIy = (float)(OUTP(kp + 1, lm, c) - OUTP(km - 1, lm, c)) * 2.0f;
+                                    else gIy = (float)(OUTP(kp + 1, lm, c) - OUTP(km, lm, c));
+                                } else {
+                                    if (fu) gIy = (float)(OUTP(kp, lm, c) - OUTP(km - 1, lm, c));
+                                    else gIy = 0;
+                                }
+                                term[c * 4 + 0] = w * (float)OUTP(k - 1, l - 1, c);
+                                term[c * 4 + 1] = -(w * (gIx * rx));
+                                term[c * 4 + 2] = -(w * (gIy * ry));
+                                term[c * 4 + 3] = w;
+                            }
+                        } else {
+                            float ry = (float)(k - i), rx = (float)(l - j);
+                            float vl = rx * rx + ry * ry;
+                            float dst = 1 / (vl * vl + 1);
+#pragma unroll
+                            for (int c = 0; c < CN; c++) {
+                                float gIx, gIy;
+                                if (fd) {
+                                    if (fu) gIx = (float)(abs(OUTP(kp + 1, lm, c) - OUTP(kp, lm, c)) + abs(OUTP(kp, lm, c) - OUTP(km - 1, lm, c)));
+                                    else gIx = (float)(abs(OUTP(kp + 1, lm, c) - OUTP(kp, lm, c))) * 2.0f;
+                                } else {
+                                    if (fu) gIx = (float)(abs(OUTP(kp, lm, c) - OUTP(km - 1, lm, c))) * 2.0f;
+                                    else gIx = 0;
+                                }
+                                if (fr) {
+                                    if (fl) gIy = (float)(abs(OUTP(km, lp + 1, c) - OUTP(km, lm, c)) + abs(OUTP(km, lm, c) - OUTP(km, lm - 1, c)));
+                                    else gIy = (float)(abs(OUTP(km, lp + 1, c) - OUTP(km, lm, c))) * 2.0f;
+                                } else {
+                                    if (fl) gIy = (float)(abs(OUTP(km, lm, c) - OUTP(km, lm - 1, c))) * 2.0f;
+                                    else gIy = 0;
+                                }
+                                gIx = -gIx;
+                                float dir = rx * gIx + ry * gIy;
+                                if (fabs(dir) <= 0.01) dir = 0.000001f;
+                                else dir = fabsf((rx * gIx + ry * gIy) / sqrtf(vl * (gIx * gIx + gIy * gIy)));
+                                float w = dst * dir;
+                                term[c * 2 + 0] = w * (float)OUTP(k - 1, l - 1, c);
+                                term[c * 2 + 1] = w;
+                            }
+                        }
+                    }
+                }
+            }
+#undef OUTP
+#undef TV
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+            for (int a = 0; a < NACC; a++) s_term[lane][a] = valid ? term[a] : 0.f;
+            __syncwarp();
+            if (lane < NACC) {
+                // the 32 terms of this accumulator into registers (independent loads), then the ordered sum
+                float v[32];
+#pragma unroll
+                for (int q = 0; q < 32; q++) v[q] = s_term[q][lane];
+#pragma unroll
+                for (int q = 0; q < 32; q++)
+                    if ((vmask >> q) & 1u) acc = acc + v[q];
+            }
+            __syncwarp();
+        }
+
+        // finish: lane c gathers its channel's accumulators
+        uint8_t result = 0;
+        if (METHOD == OFXCV_INPAINT_TELEA) {
+            int c = lane < CN ? lane : 0;
+            float Ia = __shfl_sync(0xffffffffu, acc, c * 4 + 0);
+            float Jx = __shfl_sync(0xffffffffu, acc, c * 4 + 1);
+            float Jy = __shfl_sync(0xffffffffu, acc, c * 4 + 2);
+            float s = __shfl_sync(0xffffffffu, acc, c * 4 + 3);
+            float sat = Ia / s + (Jx + Jy) / (sqrtf(Jx * Jx + Jy * Jy) + 1.0e-20f) + 0.5f;
+            int iv = __double2int_rn((double)sat);
+            result = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+        } else {
+            int c = lane < CN ? lane : 0;
+            float Ia = __shfl_sync(0xffffffffu, acc, c * 2 + 0);
+            float s = __shfl_sync(0xffffffffu, acc, c * 2 + 1);
+            int iv = __double2int_rn((double)Ia / s);
+            result = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+        }
+        if (lane < CN) {
+            volatile uint8_t* o = out + (size_t)(i - 1) * ostride + (size_t)(j - 1) * CN + lane;
+            *o = result;
+        }
+        __syncwarp();
+        __threadfence();
+        if (lane == 0) vdone[id] = 1;
+    }
+}
+
 struct IpCounters {
     unsigned nholes, tau_bits, n_new, pending, ticket, pad[3];
 };
@@ -495,6 +724,7 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
     const int nblk = ofxcv_div_up(g.np, 256);
     uint64_t launches0 = ctx->launches;
     int64_t batches = 0, rounds_total = 0;
+    ofxcv_prof_scope ps_all(ctx, s, "ip_total", 0);
     OFXCV_CUDA(ctx, cudaMemsetAsync(ctr, 0, sizeof(IpCounters), s));
     ip_init<<<nblk, 256, 0, s>>>(mask, mask_stride, hole, t, cnt, rnd, done, &ctr->nholes, g);
     OFXCV_LAUNCH_CHECK(ctx);
@@ -522,6 +752,7 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
         OFXCV_LAUNCH_CHECK(ctx);
         uint32_t next_cnt = (uint32_t)g.np;  // reached pixels get counters above every band counter
         for (;;) {
+            ofxcv_prof_scope ps(ctx, s, "ip_march_batch", pass);
             OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->tau_bits, 0xff, sizeof(unsigned), s));
             OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->n_new, 0, sizeof(unsigned), s));
             ip_pass_a<<<nblk, 256, 0, s>>>(st, t, &ctr->tau_bits, g);
@@ -571,8 +802,23 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
         int blocks = ctx->num_sms * 8;
         int need = ofxcv_div_up((int)nfilled, IP_WARPS);
         if (blocks > need) blocks = need;
+        ofxcv_prof_scope ps(ctx, s, "ip_fill", 0);
         ofxcv_time_begin(ctx, 1, s);
-#define IP_FILL(M, C) ip_fill<M, C><<<blocks, IP_WARPS * 32, 0, s>>>(order, nfilled, (uint32_t)g.np, hole, cnt, t, out, out_stride, done, &ctr->ticket, range, g)
+        const bool v2 = range <= IP2_MAXR && !getenv("OFXCV_IP_FILL_V1");
+        const int nbox_pad = ((2 * range + 3) * (2 * range + 3) + 3) & ~3;
+        const size_t fill_smem = v2 ? ((size_t)nbox_pad * 8 + 32 * (IP_MAXACC + 1) * 4) * IP_WARPS : 0;
+#define IP_FILL(M, C)                                                                                                              \
+    do {                                                                                                                           \
+        if (v2) {                                                                                                                  \
+            if (fill_smem > 48 * 1024)                                                                                             \
+                OFXCV_CUDA(ctx, cudaFuncSetAttribute(ip_fill2<M, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem)); \
+            ip_fill2<M, C><<<blocks, IP_WARPS * 32, fill_smem, s>>>(order, nfilled, (uint32_t)g.np, hole, cnt, t, out, out_stride, \
+                                                                    done, &ctr->ticket, range, g);                                 \
+        } else {                                                                                                                   \
+            ip_fill<M, C><<<blocks, IP_WARPS * 32, 0, s>>>(order, nfilled, (uint32_t)g.np, hole, cnt, t, out, out_stride, done,    \
+                                                           &ctr->ticket, range, g);                                                \
+        }                                                                                                                          \
+    } while (0)
         if (method == OFXCV_INPAINT_TELEA) {
             if (channels == 3) IP_FILL(OFXCV_INPAINT_TELEA, 3);
             else IP_FILL(OFXCV_INPAINT_TELEA, 1);
