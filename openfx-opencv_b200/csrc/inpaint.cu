@@ -444,6 +444,17 @@ ip_fill(const uint32_t* __restrict__ order, unsigned nfill, uint32_t cnt_base, c
     }
 }
 
+// fidx[n] = position of hole pixel n in the fill order, -1 for every other map position: "known at the fill time of
+// ticket tk" is then fidx[n] < tk and "earlier-filled hole" is 0 <= fidx[n] < tk -- one load instead of hole + cnt
+__global__ void __launch_bounds__(256) ip_fill_index(const uint8_t* __restrict__ hole, const uint32_t* __restrict__ cnt,
+                                                     uint32_t cnt_base, int32_t* __restrict__ fidx, IpGeom g)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= g.np) return;
+    // a hole pixel the march never reached (cnt == CNT_NONE) is never filled: it stays "not known" for everyone
+    fidx[id] = hole[id] ? (cnt[id] == CNT_NONE ? 0x7fffffff : (int32_t)(cnt[id] - cnt_base)) : -1;
+}
+
 // ---- Stage B, second generation: the (2r+3)^2 neighbourhood of the pixel is staged in shared memory ----------------
 // ip_fill above issues ~1700 dependent L2 loads per pixel from inside the tap arithmetic (8 us per pixel), and the
 // fill order of an iid mask is a dependency chain thousands of pixels long (a pixel waits for every earlier-filled
@@ -456,11 +467,11 @@ constexpr int IP2_MAXR = 10;
 
 template <int METHOD, int CN>
 __global__ void __launch_bounds__(IP_WARPS * 32)
-ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, uint32_t cnt_base, const uint8_t* __restrict__ hole,
-         const uint32_t* __restrict__ cnt, const float* __restrict__ t, uint8_t* out, ptrdiff_t ostride, uint8_t* done,
-         unsigned* __restrict__ ticket, int range, IpGeom g)
+ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __restrict__ fidx, const float* __restrict__ t,
+         uint8_t* out, ptrdiff_t ostride, uint8_t* done, unsigned* __restrict__ ticket, int range, IpGeom g)
 {
     constexpr int NACC = METHOD == OFXCV_INPAINT_TELEA ? 4 * CN : 2 * CN;
+    constexpr int PER_LANE = 4;  // box positions per lane handled with all loads in flight at once (r <= 4); more loop
     extern __shared__ __align__(16) unsigned char ip2_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ec = g.ec, er = g.er;
@@ -474,49 +485,74 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, uint32_t cnt_base, 
     float(*s_term)[IP_MAXACC + 1] = reinterpret_cast<float(*)[IP_MAXACC + 1]>(s_t + nbox_pad);
     volatile uint8_t* vdone = done;
 
+    // a ticket is taken only when the warp is free: the fill order is a dependency chain thousands of pixels long, and a
+    // ticket parked on a busy warp (tried: tickets one pixel ahead) delays everything behind it
     for (;;) {
         unsigned tk = 0;
         if (lane == 0) tk = atomicAdd(ticket, 1u);
         tk = __shfl_sync(0xffffffffu, tk, 0);
         if (tk >= nfill) break;
         const int id = (int)order[tk];
-        const uint32_t mycnt = cnt_base + tk;
         const int i = id / ec, j = id - i * ec;
         const int k0 = i - range - 1, l0 = j - range - 1;  // map coordinates of box position (0, 0)
 
-        // (a) hole / cnt of the box in one round; spin on the earlier-filled holes only
-        for (int b = lane; b < nbox; b += 32) {
-            const int bk = b / bside, bl = b - bk * bside;
-            const int k = k0 + bk, l = l0 + bl;
-            unsigned known = 1;
-            if (k >= 0 && l >= 0 && k < er && l < ec) {
-                const int n = k * ec + l;
-                if (hole[n]) {
-                    if (cnt[n] < mycnt) {
-                        while (vdone[n] == 0) { }
-                    } else {
-                        known = 0;
-                    }
+        // (a) fill index of every box position in one round; spin on the earlier-filled holes only
+        for (int b0 = 0; b0 < nbox; b0 += 32 * PER_LANE) {
+            int fi[PER_LANE], nn[PER_LANE];
+#pragma unroll
+            for (int q = 0; q < PER_LANE; q++) {
+                const int b = b0 + q * 32 + lane;
+                const int bk = b / bside, bl = b - bk * bside;
+                const int k = k0 + bk, l = l0 + bl;
+                fi[q] = -1;
+                nn[q] = -1;
+                if (b < nbox && k >= 0 && l >= 0 && k < er && l < ec) {
+                    nn[q] = k * ec + l;
+                    fi[q] = __ldg(fidx + nn[q]);
                 }
             }
-            s_px[b] = known << 24;
+#pragma unroll
+            for (int q = 0; q < PER_LANE; q++) {
+                const int b = b0 + q * 32 + lane;
+                if (b < nbox) {
+                    const bool earlier = fi[q] >= 0 && fi[q] < (int)tk;
+                    if (earlier) {
+                        while (vdone[nn[q]] == 0) { }
+                    }
+                    s_px[b] = (fi[q] < (int)tk ? 1u : 0u) << 24;
+                }
+            }
         }
         __syncwarp();
         __threadfence();
         // (b) colours (+T) of the box in one round
-        for (int b = lane; b < nbox; b += 32) {
-            const int bk = b / bside, bl = b - bk * bside;
-            const int k = k0 + bk, l = l0 + bl;
-            uint32_t px = s_px[b];
-            float tv = 0.f;
-            if (k >= 1 && l >= 1 && k <= g.H && l <= g.W) {
-                const uint8_t* o = out + (size_t)(k - 1) * ostride + (size_t)(l - 1) * CN;
+        for (int b0 = 0; b0 < nbox; b0 += 32 * PER_LANE) {
+            uint32_t px[PER_LANE];
+            float tv[PER_LANE];
 #pragma unroll
-                for (int c = 0; c < CN; c++) px |= (uint32_t)ld_u8_cg(o + c) << (8 * c);
+            for (int q = 0; q < PER_LANE; q++) {
+                const int b = b0 + q * 32 + lane;
+                const int bk = b / bside, bl = b - bk * bside;
+                const int k = k0 + bk, l = l0 + bl;
+                px[q] = 0;
+                tv[q] = 0.f;
+                if (b < nbox) {
+                    if (k >= 1 && l >= 1 && k <= g.H && l <= g.W) {
+                        const uint8_t* o = out + (size_t)(k - 1) * ostride + (size_t)(l - 1) * CN;
+#pragma unroll
+                        for (int c = 0; c < CN; c++) px[q] |= (uint32_t)ld_u8_cg(o + c) << (8 * c);
+                    }
+                    if (METHOD == OFXCV_INPAINT_TELEA && k >= 0 && l >= 0 && k < er && l < ec) tv[q] = __ldg(t + k * ec + l);
+                }
             }
-            if (METHOD == OFXCV_INPAINT_TELEA && k >= 0 && l >= 0 && k < er && l < ec) tv = t[k * ec + l];
-            s_px[b] = px;
-            s_t[b] = tv;
+#pragma unroll
+            for (int q = 0; q < PER_LANE; q++) {
+                const int b = b0 + q * 32 + lane;
+                if (b < nbox) {
+                    s_px[b] |= px[q];
+                    s_t[b] = tv[q];
+                }
+            }
         }
         __syncwarp();
 
@@ -805,6 +841,13 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
         ofxcv_prof_scope ps(ctx, s, "ip_fill", 0);
         ofxcv_time_begin(ctx, 1, s);
         const bool v2 = range <= IP2_MAXR && !getenv("OFXCV_IP_FILL_V1");
+        int32_t* fidx = nullptr;
+        if (v2) {
+            fidx = (int32_t*)ofxcv_ws(ctx, WS_INP_H, np * 4);
+            if (!fidx) return OFXCV_ERR_MEMORY;
+            ip_fill_index<<<nblk, 256, 0, s>>>(hole, cnt, (uint32_t)g.np, fidx, g);
+            OFXCV_LAUNCH_CHECK(ctx);
+        }
         const int nbox_pad = ((2 * range + 3) * (2 * range + 3) + 3) & ~3;
         const size_t fill_smem = v2 ? ((size_t)nbox_pad * 8 + 32 * (IP_MAXACC + 1) * 4) * IP_WARPS : 0;
 #define IP_FILL(M, C)                                                                                                              \
@@ -812,8 +855,8 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
         if (v2) {                                                                                                                  \
             if (fill_smem > 48 * 1024)                                                                                             \
                 OFXCV_CUDA(ctx, cudaFuncSetAttribute(ip_fill2<M, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem)); \
-            ip_fill2<M, C><<<blocks, IP_WARPS * 32, fill_smem, s>>>(order, nfilled, (uint32_t)g.np, hole, cnt, t, out, out_stride, \
-                                                                    done, &ctr->ticket, range, g);                                 \
+            ip_fill2<M, C><<<blocks, IP_WARPS * 32, fill_smem, s>>>(order, nfilled, fidx, t, out, out_stride, done, &ctr->ticket,  \
+                                                                    range, g);                                                     \
         } else {                                                                                                                   \
             ip_fill<M, C><<<blocks, IP_WARPS * 32, 0, s>>>(order, nfilled, (uint32_t)g.np, hole, cnt, t, out, out_stride, done,    \
                                                            &ctr->ticket, range, g);                                                \
