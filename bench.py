@@ -350,12 +350,14 @@ def bench_plugins(pkg, synth, ctx, W, H, with_cpu):
             ent["bytes_differing_from_cv2"] = int((got != ref).sum())
         out[name] = ent
     mk = synth.seed_markers(H, W, 256, 5)
-    for nf in (1, 64):
+    for nf in (1, 256):
         d_rgbs, d_mks = ctx.alloc(W * H * 3 * nf), ctx.alloc(W * H * 4 * nf)
         L = pkg.lib()
-        for f in range(nf):
-            L.ofxcv_upload(ctx.h, None, d_rgbs.ptr + f * W * H * 3, img.ctypes.data, W * H * 3)
-            L.ofxcv_upload(ctx.h, None, d_mks.ptr + f * W * H * 4, mk.ctypes.data, W * H * 4)
+        L.ofxcv_upload(ctx.h, None, d_rgbs.ptr, img.ctypes.data, W * H * 3)
+        L.ofxcv_upload(ctx.h, None, d_mks.ptr, mk.ctypes.data, W * H * 4)
+        for f in range(1, nf):   # the same frame nf times: replicated on the device
+            L.ofxcv_device_copy(ctx.h, None, d_rgbs.ptr + f * W * H * 3, d_rgbs.ptr, W * H * 3)
+            L.ofxcv_device_copy(ctx.h, None, d_mks.ptr + f * W * H * 4, d_mks.ptr, W * H * 4)
         ctx.synchronize()
         t = time.perf_counter()
         ctx.watershed_dev(d_rgbs.ptr, d_mks.ptr, W, H, nf)

@@ -75,6 +75,7 @@ OFXCV_API void* ofxcv_pinned_alloc(ofxcv_ctx* ctx, size_t bytes);
 OFXCV_API void ofxcv_pinned_free(ofxcv_ctx* ctx, void* hptr);
 OFXCV_API int ofxcv_upload(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, const void* src_host, size_t bytes);
 OFXCV_API int ofxcv_download(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_host, const void* src_dev, size_t bytes);
+OFXCV_API int ofxcv_device_copy(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, const void* src_dev, size_t bytes);
 OFXCV_API int ofxcv_memset(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, int value, size_t bytes);
 
 /* ---- dense optical flow ----------------------------------------------------------------------------- */

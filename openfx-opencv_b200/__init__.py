@@ -84,6 +84,7 @@ def lib():
         "ofxcv_pinned_free": (None, [vp, vp]),
         "ofxcv_upload": (i, [vp, vp, vp, vp, sz]),
         "ofxcv_download": (i, [vp, vp, vp, vp, sz]),
+        "ofxcv_device_copy": (i, [vp, vp, vp, vp, sz]),
         "ofxcv_memset": (i, [vp, vp, vp, i, sz]),
         "ofxcv_fb_default_params": (None, [fbp]),
         "ofxcv_farneback_scales": (i, [i, i, fbp]),

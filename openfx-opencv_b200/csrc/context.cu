@@ -313,6 +313,15 @@ int ofxcv_download(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_host, const void* s
     return OFXCV_OK;
 }
 
+int ofxcv_device_copy(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, const void* src_dev, size_t bytes)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!dst_dev || !src_dev) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard g(ctx->device);
+    OFXCV_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, pick(ctx, s)));
+    return OFXCV_OK;
+}
+
 int ofxcv_memset(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, int value, size_t bytes)
 {
     if (!ctx) return OFXCV_ERR_NO_DEVICE;

@@ -120,3 +120,47 @@ def test_content_key(ctx, synth):
     ka, kb, kc = (ctx.content_key(ctx.to_device(x).ptr, 80, 64) for x in (a, b, c))
     assert ka == ctx.content_key(ctx.to_device(a.copy()).ptr, 80, 64)
     assert len({ka, kb, kc}) == 3 and 0 not in (ka, kb, kc)
+
+
+@pytest.mark.parametrize("h,w,levels,iters,poly_n", [(7, 29, 0, 2, 5), (9, 8, 0, 3, 5), (40, 50, 3, 3, 5), (33, 31, 1, 2, 3), (64, 95, 2, 0, 5), (61, 62, 2, 1, 7)])
+def test_farneback_edge_shapes(ctx, pkg, oracle, synth, h, w, levels, iters, poly_n):
+    """Single strip / single band images, level clipping (< 32 px), zero and one iteration, the generic PolyExp path."""
+    prev, nxt = synth.flow_pair(h, w, seed=7, dx=1.25, dy=0.5)
+    sigma = 1.1 if poly_n == 5 else 1.5 if poly_n == 7 else 0.9
+    got = ctx.farneback(prev, nxt, pkg.FbParams(levels=levels, iterations=iters, poly_n=poly_n, poly_sigma=sigma))
+    ref = oracle.farneback(prev, nxt, levels=levels, iters=iters, poly_n=poly_n, poly_sigma=sigma)
+    mean, f2, f0, same = _stats(got, ref)
+    assert mean <= STRICT_MEAN and f2 <= STRICT_FRAC_1E2 and f0 <= 2e-4, (mean, f2, f0, same)
+
+
+def test_farneback_strided_device_buffers(ctx, pkg, oracle, synth):
+    """Device entry point with row padding on both frames and on the flow field (OFX rowBytes > width)."""
+    h, w, pad, fpad = 70, 101, 27, 40
+    prev, nxt = synth.flow_pair(h, w, seed=9)
+    buf = np.full((2, h, w + pad), 123, np.uint8)
+    buf[0, :, :w], buf[1, :, :w] = prev, nxt
+    d = ctx.to_device(buf)
+    fstride = w * 8 + fpad
+    d_flow = ctx.alloc(h * fstride)
+    p = pkg.FbParams(levels=2, iterations=3)
+    ctx.farneback_dev(d.ptr, d.ptr + h * (w + pad), w, h, d_flow.ptr, p, stride=w + pad, flow_stride=fstride)
+    ctx.synchronize()
+    raw = d_flow.download((h, fstride), np.uint8)
+    got = np.ascontiguousarray(raw[:, :w * 8]).view(np.float32).reshape(h, w, 2)
+    ref = oracle.farneback(prev, nxt, levels=2, iters=3)
+    assert np.abs(got - ref).max(axis=2).mean() <= STRICT_MEAN
+
+
+def test_farneback_4k_properties(ctx, pkg, synth):
+    """BASELINE config size (3840x2160, default parameters): size-independent properties instead of the (slow) oracle --
+    the known global translation is recovered, two runs give identical bits, the clip call equals the pair call."""
+    h, w = 2160, 3840
+    base = synth.gray(synth.texture(h, w, seed=2000))
+    f = [base, synth.shift_bilinear(base, 2.5, -1.5), synth.shift_bilinear(base, 5.0, -3.0)]
+    a = ctx.farneback(f[0], f[1])
+    b = ctx.farneback(f[0], f[1])
+    assert np.array_equal(a, b)
+    epe = np.hypot(a[200:-200, 200:-200, 0] - 2.5, a[200:-200, 200:-200, 1] + 1.5)
+    assert epe.mean() < 0.5 and np.median(epe) < 0.3, (epe.mean(), np.median(epe))   # u8 texture, polyN 5: ~0.2 px
+    seq = ctx.farneback_sequence(f)
+    assert np.array_equal(seq[0], a) and np.array_equal(seq[1], ctx.farneback(f[1], f[2]))
