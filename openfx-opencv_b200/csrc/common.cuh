@@ -63,7 +63,7 @@ struct ofxcv_ctx {
     // copy streams + events of the *_sequence_host entry points (created on first use)
     cudaStream_t stream_up = nullptr, stream_down = nullptr, stream_lane[2] = {nullptr, nullptr};
     cudaEvent_t lane_done[2] = {nullptr, nullptr}, lane_start = nullptr;
-    cudaEvent_t seq_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t seq_ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int64_t inpaint_stats[4] = {0, 0, 0, 0};
     int64_t watershed_stats[4] = {0, 0, 0, 0};
 };

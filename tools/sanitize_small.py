@@ -1,0 +1,22 @@
+"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck).
+usage: compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+import importlib, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+p = importlib.import_module("openfx-opencv_b200"); s = importlib.import_module("openfx-opencv_b200.synth")
+ctx = p.Context(0)
+for (h, w, lv, it) in ((7, 29, 0, 2), (61, 62, 2, 3), (135, 241, 3, 4), (270, 480, 3, 3), (600, 1100, 2, 2)):
+    a, b = s.flow_pair(h, w, seed=3)
+    f = ctx.farneback(a, b, p.FbParams(levels=lv, iterations=it))
+    assert np.isfinite(f).all()
+frames = [s.shift_bilinear(s.gray(s.texture(90, 130, 5)), 1.0 * i, 0.5 * i) for i in range(4)]
+ctx.farneback_sequence(frames, p.FbParams(levels=2, iterations=3))
+img = s.texture(60, 80, 1)
+for m in (p.INPAINT_NS, p.INPAINT_TELEA):
+    ctx.inpaint(img, s.iid_mask(60, 80, 2, 0.1), 3, m)
+    ctx.inpaint(img, s.blob_mask(60, 80, 3), 5, m)
+ctx.watershed(img, s.seed_markers(60, 80, 5, 5))
+rgba = np.random.default_rng(0).random((33, 47, 4), dtype=np.float32)
+ctx.rgba32f_to_srgb_gray8(rgba); ctx.rgba32f_to_srgb8_packed(rgba, 4); ctx.srgb8_packed_to_rgba32f((rgba * 255).astype(np.uint8))
+ctx.close()
+print("sanitize_small: done")
