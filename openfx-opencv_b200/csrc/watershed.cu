@@ -14,6 +14,8 @@
 //                  comes from many frames in flight per SM (ofxcv_watershed_u8c3_batch).
 // Per-frame state: nxt int32 (intrusive FIFO link, every pixel is queued at most once) + pix u32, pitch = the
 // marker pitch.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -200,6 +202,110 @@ __global__ void __launch_bounds__(32) ws_flood(int32_t* __restrict__ m, ptrdiff_
     pops_out[f] = pops;
 }
 
+// one thread per frame, software-pipelined: the FIFO link of the pixel being popped names the pixel that will be
+// popped next unless this pop pushes to a lower level or empties the queue, so its ten loads are issued BEFORE the
+// label / push work of the current pop and land behind it (one memory latency and one ALU chain per pop overlap
+// instead of adding up).  The prefetched labels are patched in registers with what the current pop changes (its own
+// label, the IN_QUEUE marks of the pixels it pushes, the link it appends behind the prefetched pixel), so the flood is
+// exactly the sequential one.
+__global__ void __launch_bounds__(32) ws_flood2(int32_t* __restrict__ m, ptrdiff_t ms_, size_t m_frame,
+                                                const uint32_t* __restrict__ pix, int32_t* __restrict__ nxt, size_t st_frame,
+                                                const int32_t* __restrict__ heads, unsigned long long* __restrict__ pops_out)
+{
+    __shared__ int32_t head[256], tail[256];
+    const int f = blockIdx.x;
+    for (int i = threadIdx.x; i < 256; i += 32) {
+        head[i] = heads[(size_t)f * 512 + i];
+        tail[i] = heads[(size_t)f * 512 + 256 + i];
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    int32_t* mf = m + f * m_frame;
+    const uint32_t* pf = pix + f * st_frame;
+    int32_t* nf = nxt + f * st_frame;
+    const int ms = (int)ms_;
+    unsigned long long pops = 0;
+    int active = 0;
+    while (active < 256 && head[active] < 0) active++;
+    if (active < 256) {
+        int32_t p = head[active];
+        // the current pop's loads
+        int32_t np = nf[p];
+        int32_t ml = mf[p - 1], mr = mf[p + 1], mu = mf[p - ms], md = mf[p + ms];
+        uint32_t c = pf[p], cl = pf[p - 1], cr = pf[p + 1], cu = pf[p - ms], cd = pf[p + ms];
+        for (;;) {
+            // prefetch the predicted next pop (the next entry of the active queue)
+            const int32_t pn = np;
+            int32_t n2 = -1, nl = 0, nr = 0, nu = 0, nd = 0;
+            uint32_t e = 0, el = 0, er_ = 0, eu = 0, ed = 0;
+            if (pn >= 0) {
+                n2 = nf[pn];
+                nl = mf[pn - 1]; nr = mf[pn + 1]; nu = mf[pn - ms]; nd = mf[pn + ms];
+                e = pf[pn]; el = pf[pn - 1]; er_ = pf[pn + 1]; eu = pf[pn - ms]; ed = pf[pn + ms];
+            }
+            // ---- the pop of p -------------------------------------------------------------------------------
+            head[active] = np;
+            pops++;
+            int lab = 0;
+            if (ml > 0) lab = ml;
+            if (mr > 0) { if (lab == 0) lab = mr; else if (mr != lab) lab = WS_WSHED; }
+            if (mu > 0) { if (lab == 0) lab = mu; else if (mu != lab) lab = WS_WSHED; }
+            if (md > 0) { if (lab == 0) lab = md; else if (md != lab) lab = WS_WSHED; }
+            mf[p] = lab;
+            // p's label as seen by the prefetched pixel
+            if (pn - 1 == p) nl = lab;
+            if (pn + 1 == p) nr = lab;
+            if (pn - ms == p) nu = lab;
+            if (pn + ms == p) nd = lab;
+            const int level_at_pop = active;
+            if (lab != WS_WSHED) {
+#define WS_PUSH2(cond, q, cq)                                        \
+    if (cond) {                                                      \
+        const int t = pixdiff(c, cq);                                \
+        nf[q] = -1;                                                  \
+        if (head[t] < 0) head[t] = (q);                              \
+        else {                                                       \
+            if (tail[t] == pn) n2 = (q); /* appended behind the prefetched pixel */ \
+            nf[tail[t]] = (q);                                       \
+        }                                                            \
+        tail[t] = (q);                                               \
+        if (t < active) active = t;                                  \
+        mf[q] = WS_IN_QUEUE;                                         \
+        if (pn - 1 == (q)) nl = WS_IN_QUEUE;                         \
+        if (pn + 1 == (q)) nr = WS_IN_QUEUE;                         \
+        if (pn - ms == (q)) nu = WS_IN_QUEUE;                        \
+        if (pn + ms == (q)) nd = WS_IN_QUEUE;                        \
+    }
+                WS_PUSH2(ml == 0, p - 1, cl)
+                WS_PUSH2(mr == 0, p + 1, cr)
+                WS_PUSH2(mu == 0, p - ms, cu)
+                WS_PUSH2(md == 0, p + ms, cd)
+#undef WS_PUSH2
+            }
+            // ---- who is next? -------------------------------------------------------------------------------
+            if (active == level_at_pop && pn >= 0) {
+                // the prediction holds: continue with the prefetched (and patched) registers
+                p = pn;
+                np = n2;
+                ml = nl; mr = nr; mu = nu; md = nd;
+                c = e; cl = el; cr = er_; cu = eu; cd = ed;
+                continue;
+            }
+            if (head[active] < 0) {
+                int i = active + 1;
+                while (i < 256 && head[i] < 0) i++;
+                if (i == 256) break;
+                active = i;
+            }
+            p = head[active];
+            np = nf[p];
+            ml = mf[p - 1]; mr = mf[p + 1]; mu = mf[p - ms]; md = mf[p + ms];
+            c = pf[p]; cl = pf[p - 1]; cr = pf[p + 1]; cu = pf[p - ms]; cd = pf[p + ms];
+        }
+    }
+    pops_out[f] = pops;
+}
+
 }  // namespace
 
 extern "C" {
@@ -236,7 +342,8 @@ int ofxcv_watershed_u8c3_batch(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8
     ws_link<<<nframes, 1024, 0, s>>>(markers, ms, m_frame, nxt, st_frame, heads, W, H);
     OFXCV_LAUNCH_CHECK(ctx);
     ofxcv_time_begin(ctx, 2, s);
-    ws_flood<<<nframes, 32, 0, s>>>(markers, ms, m_frame, pix, nxt, st_frame, heads, pops);
+    if (getenv("OFXCV_WS_FLOOD_V1")) ws_flood<<<nframes, 32, 0, s>>>(markers, ms, m_frame, pix, nxt, st_frame, heads, pops);
+    else ws_flood2<<<nframes, 32, 0, s>>>(markers, ms, m_frame, pix, nxt, st_frame, heads, pops);
     ofxcv_time_end(ctx, 2, s);
     OFXCV_LAUNCH_CHECK(ctx);
     ctx->watershed_stats[0] = -1;  // resolved lazily by ofxcv_watershed_last_stats
