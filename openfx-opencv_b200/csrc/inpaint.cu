@@ -517,14 +517,17 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __re
                 if (b < nbox) {
                     const bool earlier = fi[q] >= 0 && fi[q] < (int)tk;
                     if (earlier) {
-                        while (vdone[nn[q]] == 0) { }
+                        // acquire load: what the finished pixel's warp wrote before its release is visible after it
+                        unsigned d;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(d) : "l"(done + nn[q]) : "memory");
+                        } while (d == 0);
                     }
                     s_px[b] = (fi[q] < (int)tk ? 1u : 0u) << 24;
                 }
             }
         }
-        __syncwarp();
-        __threadfence();
+        __syncwarp();  // orders every lane's loads below after the acquire loads of the lanes that waited
         // (b) colours (+T) of the box in one round
         for (int b0 = 0; b0 < nbox; b0 += 32 * PER_LANE) {
             uint32_t px[PER_LANE];
@@ -703,8 +706,9 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __re
             *o = result;
         }
         __syncwarp();
-        __threadfence();
-        if (lane == 0) vdone[id] = 1;
+        if (lane == 0) {  // release: the colour bytes stored by lanes 0..CN-1 (ordered by the barrier above) before the flag
+            asm volatile("st.release.gpu.global.u8 [%0], %1;" ::"l"(done + id), "r"(1u) : "memory");
+        }
     }
 }
 
