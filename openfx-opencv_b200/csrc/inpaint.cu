@@ -517,11 +517,11 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __re
                 if (b < nbox) {
                     const bool earlier = fi[q] >= 0 && fi[q] < (int)tk;
                     if (earlier) {
+                        // poll relaxed (an acquire load drags a CCTL.IVALL = L1 invalidate into every iteration), then ONE
                         // acquire load: what the finished pixel's warp wrote before its release is visible after it
+                        while (vdone[nn[q]] == 0) { }
                         unsigned d;
-                        do {
-                            asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(d) : "l"(done + nn[q]) : "memory");
-                        } while (d == 0);
+                        asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(d) : "l"(done + nn[q]) : "memory");
                     }
                     s_px[b] = (fi[q] < (int)tk ? 1u : 0u) << 24;
                 }
