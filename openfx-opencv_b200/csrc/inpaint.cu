@@ -455,23 +455,31 @@ __global__ void __launch_bounds__(256) ip_fill_index(const uint8_t* __restrict__
     fidx[id] = hole[id] ? (cnt[id] == CNT_NONE ? 0x7fffffff : (int32_t)(cnt[id] - cnt_base)) : -1;
 }
 
-// ---- Stage B, second generation: the (2r+3)^2 neighbourhood of the pixel is staged in shared memory ----------------
-// ip_fill above issues ~1700 dependent L2 loads per pixel from inside the tap arithmetic (8 us per pixel), and the
-// fill order of an iid mask is a dependency chain thousands of pixels long (a pixel waits for every earlier-filled
-// hole pixel of its box), so the kernel runs at chain length x per-pixel latency.  Here a warp (a) loads hole/cnt of
-// the whole box in one round and spins only on the positions that are earlier-filled holes, (b) loads the colours
-// (+T for Telea) of the box in one more round into shared memory with the "known" flag packed beside them, (c)
-// evaluates the taps from shared memory only, and (d) sums the accumulators in tap order from registers.  Same
-// arithmetic, ~4x shorter per-pixel latency.  Used for radius <= IP2_MAXR (the plugin's range is [1, 10]).
+// ---- Stage B, staged: the (2r+3)^2 neighbourhood of the pixel lives in shared memory --------------------------------
+// ip_fill above issues ~1700 dependent L2 loads per pixel from inside the tap arithmetic, and the fill order is a
+// dependency chain thousands of pixels long (a pixel needs every earlier-filled hole pixel of its box), so the kernel
+// runs at chain length x per-pixel latency.  Here a warp (a) loads the fill index of the whole box in one round --
+// "known at this pixel's fill time" is fidx < tk --, (b) loads the colours (+T for Telea) of the box in one more round
+// into shared memory with the known flag packed beside them, (c) evaluates the taps from shared memory only, with the
+// tap / box geometry of each lane computed once per warp and constant offsets for pixels away from the image border
+// (the per-pixel instruction count IS the chain latency: one warp executes it serially), and (d) sums the accumulators
+// in tap order from registers.  Same arithmetic as ip_fill.  Two schedulers:
+//   READYQ = false: tickets in fill order, a warp spins on the done flags of the earlier-filled holes of its box;
+//   READYQ = true : dependency counters + a ready queue -- a warp only ever waits for a queue slot, so independent
+//                   dependency chains advance in parallel even when the fill order lays them out one after the other
+//                   (scratches, several blobs); costs ~2 us more per chain step.
+// Used for radius <= IP2_MAXR (the plugin's range is [1, 10]).
 constexpr int IP2_MAXR = 10;
+constexpr int IP2_NPOS = 4;  // box positions per lane kept in flight / tabulated (covers r <= 4: 121 positions)
+constexpr int IP2_NTAP = 3;  // taps per lane tabulated (covers r <= 4: 81 taps)
 
-template <int METHOD, int CN>
+template <int METHOD, int CN, bool READYQ>
 __global__ void __launch_bounds__(IP_WARPS * 32)
-ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __restrict__ fidx, const float* __restrict__ t,
-         uint8_t* out, ptrdiff_t ostride, uint8_t* done, unsigned* __restrict__ ticket, int range, IpGeom g)
+ip_fill_staged(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __restrict__ fidx, const float* __restrict__ t,
+               uint8_t* out, ptrdiff_t ostride, uint8_t* done, int32_t* dep, int32_t* rq, unsigned* __restrict__ ticket,
+               unsigned* __restrict__ rtail, int range, IpGeom g)
 {
     constexpr int NACC = METHOD == OFXCV_INPAINT_TELEA ? 4 * CN : 2 * CN;
-    constexpr int PER_LANE = 4;  // box positions per lane handled with all loads in flight at once (r <= 4); more loop
     extern __shared__ __align__(16) unsigned char ip2_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ec = g.ec, er = g.er;
@@ -485,76 +493,118 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __re
     float(*s_term)[IP_MAXACC + 1] = reinterpret_cast<float(*)[IP_MAXACC + 1]>(s_t + nbox_pad);
     volatile uint8_t* vdone = done;
 
-    // a ticket is taken only when the warp is free: the fill order is a dependency chain thousands of pixels long, and a
-    // ticket parked on a busy warp (tried: tickets one pixel ahead) delays everything behind it
+    // geometry of this lane's box positions and taps: the same for every pixel
+    const bool tabulated = nbox <= 32 * IP2_NPOS && ntaps <= 32 * IP2_NTAP;
+    int pk[IP2_NPOS], pl[IP2_NPOS];  // box position -> offset from the box origin (row, col); row < 0 = none
+#pragma unroll
+    for (int q = 0; q < IP2_NPOS; q++) {
+        const int b = q * 32 + lane;
+        pk[q] = b < nbox ? b / bside : -1;
+        pl[q] = b < nbox ? b - (b / bside) * bside : 0;
+    }
+    int tdk[IP2_NTAP], tdl[IP2_NTAP];  // tap -> offset from the pixel; tdk = INT_MIN/2 = no tap / outside the disc
+#pragma unroll
+    for (int u = 0; u < IP2_NTAP; u++) {
+        const int tp = u * 32 + lane;
+        const int dk = tp / side - range, dl = tp % side - range;
+        const bool in = tp < ntaps && dk * dk + dl * dl <= range * range;
+        tdk[u] = in ? dk : -(1 << 20);
+        tdl[u] = dl;
+    }
+
     for (;;) {
-        unsigned tk = 0;
-        if (lane == 0) tk = atomicAdd(ticket, 1u);
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        if (tk >= nfill) break;
-        const int id = (int)order[tk];
+        unsigned tk;
+        int id;
+        if (!READYQ) {
+            // a ticket is taken only when the warp is free: a ticket parked on a busy warp (tried: tickets one pixel ahead)
+            // delays the whole chain behind it
+            unsigned v = 0;
+            if (lane == 0) v = atomicAdd(ticket, 1u);
+            tk = __shfl_sync(0xffffffffu, v, 0);
+            if (tk >= nfill) break;
+            id = (int)order[tk];
+        } else {
+            unsigned my = 0;
+            if (lane == 0) my = atomicAdd(ticket, 1u);
+            my = __shfl_sync(0xffffffffu, my, 0);
+            if (my >= nfill) break;
+            int got = 0;
+            if (lane == 0) {
+                volatile int32_t* slot = rq + my;
+                while (*slot < 0) { }
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(rq + my) : "memory");
+            }
+            id = __shfl_sync(0xffffffffu, got, 0);  // the shuffle orders every lane after the acquire
+            tk = (unsigned)__ldg(fidx + id);
+        }
         const int i = id / ec, j = id - i * ec;
         const int k0 = i - range - 1, l0 = j - range - 1;  // map coordinates of box position (0, 0)
 
-        // (a) fill index of every box position in one round; spin on the earlier-filled holes only
-        for (int b0 = 0; b0 < nbox; b0 += 32 * PER_LANE) {
-            int fi[PER_LANE], nn[PER_LANE];
-#pragma unroll
-            for (int q = 0; q < PER_LANE; q++) {
-                const int b = b0 + q * 32 + lane;
-                const int bk = b / bside, bl = b - bk * bside;
-                const int k = k0 + bk, l = l0 + bl;
-                fi[q] = -1;
-                nn[q] = -1;
-                if (b < nbox && k >= 0 && l >= 0 && k < er && l < ec) {
-                    nn[q] = k * ec + l;
-                    fi[q] = __ldg(fidx + nn[q]);
-                }
+        // (a) fill index of every box position in one round (SPIN: wait for the earlier-filled holes among them)
+        auto stage_a = [&](int b, int k, int l, int& fi, int& n) {
+            fi = -1;
+            n = -1;
+            if (k >= 0 && l >= 0 && k < er && l < ec) {
+                n = k * ec + l;
+                fi = __ldg(fidx + n);
             }
-#pragma unroll
-            for (int q = 0; q < PER_LANE; q++) {
-                const int b = b0 + q * 32 + lane;
-                if (b < nbox) {
-                    const bool earlier = fi[q] >= 0 && fi[q] < (int)tk;
-                    if (earlier) {
-                        // poll relaxed (an acquire load drags a CCTL.IVALL = L1 invalidate into every iteration), then ONE
-                        // acquire load: what the finished pixel's warp wrote before its release is visible after it
-                        while (vdone[nn[q]] == 0) { }
-                        unsigned d;
-                        asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(d) : "l"(done + nn[q]) : "memory");
-                    }
-                    s_px[b] = (fi[q] < (int)tk ? 1u : 0u) << 24;
-                }
+        };
+        auto stage_a2 = [&](int b, int fi, int n) {
+            if (!READYQ && fi >= 0 && fi < (int)tk) {
+                // poll relaxed (an acquire load drags a CCTL.IVALL = L1 invalidate into every iteration), then ONE
+                // acquire load: what the finished pixel's warp wrote before its release is visible after it
+                while (vdone[n] == 0) { }
+                unsigned d;
+                asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(d) : "l"(done + n) : "memory");
             }
-        }
-        __syncwarp();  // orders every lane's loads below after the acquire loads of the lanes that waited
+            s_px[b] = (fi < (int)tk ? 1u : 0u) << 24;
+        };
         // (b) colours (+T) of the box in one round
-        for (int b0 = 0; b0 < nbox; b0 += 32 * PER_LANE) {
-            uint32_t px[PER_LANE];
-            float tv[PER_LANE];
+        auto stage_b = [&](int k, int l, uint32_t& px, float& tv) {
+            px = 0;
+            tv = 0.f;
+            if (k >= 1 && l >= 1 && k <= g.H && l <= g.W) {
+                const uint8_t* o = out + (size_t)(k - 1) * ostride + (size_t)(l - 1) * CN;
 #pragma unroll
-            for (int q = 0; q < PER_LANE; q++) {
-                const int b = b0 + q * 32 + lane;
-                const int bk = b / bside, bl = b - bk * bside;
-                const int k = k0 + bk, l = l0 + bl;
-                px[q] = 0;
-                tv[q] = 0.f;
-                if (b < nbox) {
-                    if (k >= 1 && l >= 1 && k <= g.H && l <= g.W) {
-                        const uint8_t* o = out + (size_t)(k - 1) * ostride + (size_t)(l - 1) * CN;
-#pragma unroll
-                        for (int c = 0; c < CN; c++) px[q] |= (uint32_t)ld_u8_cg(o + c) << (8 * c);
-                    }
-                    if (METHOD == OFXCV_INPAINT_TELEA && k >= 0 && l >= 0 && k < er && l < ec) tv[q] = __ldg(t + k * ec + l);
-                }
+                for (int c = 0; c < CN; c++) px |= (uint32_t)ld_u8_cg(o + c) << (8 * c);
             }
+            if (METHOD == OFXCV_INPAINT_TELEA && k >= 0 && l >= 0 && k < er && l < ec) tv = __ldg(t + k * ec + l);
+        };
+        if (tabulated) {
+            int fi[IP2_NPOS], nn[IP2_NPOS];
 #pragma unroll
-            for (int q = 0; q < PER_LANE; q++) {
-                const int b = b0 + q * 32 + lane;
-                if (b < nbox) {
-                    s_px[b] |= px[q];
-                    s_t[b] = tv[q];
+            for (int q = 0; q < IP2_NPOS; q++)
+                if (pk[q] >= 0) stage_a(q * 32 + lane, k0 + pk[q], l0 + pl[q], fi[q], nn[q]);
+#pragma unroll
+            for (int q = 0; q < IP2_NPOS; q++)
+                if (pk[q] >= 0) stage_a2(q * 32 + lane, fi[q], nn[q]);
+            __syncwarp();  // orders every lane's loads below after the acquire loads of the lanes that waited
+            uint32_t px[IP2_NPOS];
+            float tv[IP2_NPOS];
+#pragma unroll
+            for (int q = 0; q < IP2_NPOS; q++)
+                if (pk[q] >= 0) stage_b(k0 + pk[q], l0 + pl[q], px[q], tv[q]);
+#pragma unroll
+            for (int q = 0; q < IP2_NPOS; q++)
+                if (pk[q] >= 0) {
+                    s_px[q * 32 + lane] |= px[q];
+                    s_t[q * 32 + lane] = tv[q];
                 }
+        } else {
+            for (int b = lane; b < nbox; b += 32) {
+                const int bk = b / bside, bl = b - bk * bside;
+                int fi, n;
+                stage_a(b, k0 + bk, l0 + bl, fi, n);
+                stage_a2(b, fi, n);
+            }
+            __syncwarp();
+            for (int b = lane; b < nbox; b += 32) {
+                const int bk = b / bside, bl = b - bk * bside;
+                uint32_t px;
+                float tv;
+                stage_b(k0 + bk, l0 + bl, px, tv);
+                s_px[b] |= px;
+                s_t[b] = tv;
             }
         }
         __syncwarp();
@@ -564,6 +614,9 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __re
         auto known = [&](int k, int l) -> bool { return (s_px[bidx(k, l)] >> 24) != 0; };
 #define OUTP(r, c, ch) (int)((s_px[bidx((r) + 1, (c) + 1)] >> (8 * (ch))) & 0xffu)
 #define TV(k, l) s_t[bidx((k), (l))]
+// the same through a box index (pixels away from the image border: every stencil index is a constant offset)
+#define KNOWN_AT(x) ((s_px[(x)] >> 24) != 0)
+#define OUT_AT(x, ch) (int)((s_px[(x)] >> (8 * (ch))) & 0xffu)
 
         float gTx = 0.f, gTy = 0.f, ti = 0.f;
         if (METHOD == OFXCV_INPAINT_TELEA) {
@@ -588,25 +641,30 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __re
         if (METHOD == OFXCV_INPAINT_TELEA) { if ((lane & 3) == 3) acc = 1.0e-20f; }
         else { if ((lane & 1) == 1) acc = 1.0e-20f; }
 
-        for (int base = 0; base < ntaps; base += 32) {
-            const int tp = base + lane;
+        // every tap's whole stencil inside the image without clamping?
+        const bool interior = tabulated && i - range >= 2 && i + range <= g.H - 1 && j - range >= 2 && j + range <= g.W - 1;
+        const int nrounds = (ntaps + 31) >> 5;
+        for (int u = 0; u < nrounds; u++) {
             bool valid = false;
             float term[IP_MAXACC];
 #pragma unroll
             for (int a = 0; a < IP_MAXACC; a++) term[a] = 0.f;
-            if (tp < ntaps) {
-                const int k = i - range + tp / side, l = j - range + tp % side;
-                if (k > 0 && l > 0 && k < er - 1 && l < ec - 1) {
-                    if (known(k, l) && (l - j) * (l - j) + (k - i) * (k - i) <= range * range) {
+            if (interior) {
+                // u < IP2_NTAP here; the tables are indexed with compile-time constants below
+                int dk = -(1 << 20), dl = 0;
+#pragma unroll
+                for (int uu = 0; uu < IP2_NTAP; uu++)
+                    if (uu == u) { dk = tdk[uu]; dl = tdl[uu]; }
+                if (dk > -(1 << 19)) {
+                    const int x = (dk + range + 1) * bside + (dl + range + 1);  // box index of the tap
+                    if (KNOWN_AT(x)) {
                         valid = true;
-                        const int km = k - 1 + (k == 1), kp = k - 1 - (k == er - 2);
-                        const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ec - 2);
-                        const bool fr = known(k, l + 1), fl = known(k, l - 1), fd = known(k + 1, l), fu = known(k - 1, l);
+                        const bool fr = KNOWN_AT(x + 1), fl = KNOWN_AT(x - 1), fd = KNOWN_AT(x + bside), fu = KNOWN_AT(x - bside);
                         if (METHOD == OFXCV_INPAINT_TELEA) {
-                            float ry = (float)(i - k), rx = (float)(j - l);
+                            float ry = (float)(-dk), rx = (float)(-dl);
                             float vl = rx * rx + ry * ry;
                             float dst = (float)(1. / (vl * sqrt((double)vl)));
-                            float lev = (float)(1. / (1 + (double)fabsf(TV(k, l) - ti)));  // f32 difference, f64 sum (C fabs)
+                            float lev = (float)(1. / (1 + (double)fabsf(s_t[x] - ti)));  // f32 difference, f64 sum (C fabs)
                             float dir = rx * gTx + ry * gTy;
                             if (fabs(dir) <= 0.01) dir = 0.000001f;
                             float w = (float)fabs(dst * lev * dir);
@@ -614,43 +672,43 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __re
                             for (int c = 0; c < CN; c++) {
                                 float gIx, gIy;
                                 if (fr) {
-                                    if (fl) gIx = (float)(OUTP(km, lp + 1, c) - OUTP(km, lm - 1, c)) * 2.0f;
-                                    else gIx = (float)(OUTP(km, lp + 1, c) - OUTP(km, lm, c));
+                                    if (fl) gIx = (float)(OUT_AT(x + 1, c) - OUT_AT(x - 1, c)) * 2.0f;
+                                    else gIx = (float)(OUT_AT(x + 1, c) - OUT_AT(x, c));
                                 } else {
-                                    if (fl) gIx = (float)(OUTP(km, lp, c) - OUTP(km, lm - 1, c));
+                                    if (fl) gIx = (float)(OUT_AT(x, c) - OUT_AT(x - 1, c));
                                     else gIx = 0;
                                 }
                                 if (fd) {
-                                    if (fu) gIy = (float)(OUTP(kp + 1, lm, c) - OUTP(km - 1, lm, c)) * 2.0f;
-                                    else gIy = (float)(OUTP(kp + 1, lm, c) - OUTP(km, lm, c));
+                                    if (fu) gIy = (float)(OUT_AT(x + bside, c) - OUT_AT(x - bside, c)) * 2.0f;
+                                    else gIy = (float)(OUT_AT(x + bside, c) - OUT_AT(x, c));
                                 } else {
-                                    if (fu) gIy = (float)(OUTP(kp, lm, c) - OUTP(km - 1, lm, c));
+                                    if (fu) gIy = (float)(OUT_AT(x, c) - OUT_AT(x - bside, c));
                                     else gIy = 0;
                                 }
-                                term[c * 4 + 0] = w * (float)OUTP(k - 1, l - 1, c);
+                                term[c * 4 + 0] = w * (float)OUT_AT(x, c);
                                 term[c * 4 + 1] = -(w * (gIx * rx));
                                 term[c * 4 + 2] = -(w * (gIy * ry));
                                 term[c * 4 + 3] = w;
                             }
                         } else {
-                            float ry = (float)(k - i), rx = (float)(l - j);
+                            float ry = (float)dk, rx = (float)dl;
                             float vl = rx * rx + ry * ry;
                             float dst = 1 / (vl * vl + 1);
 #pragma unroll
                             for (int c = 0; c < CN; c++) {
                                 float gIx, gIy;
                                 if (fd) {
-                                    if (fu) gIx = (float)(abs(OUTP(kp + 1, lm, c) - OUTP(kp, lm, c)) + abs(OUTP(kp, lm, c) - OUTP(km - 1, lm, c)));
-                                    else gIx = (float)(abs(OUTP(kp + 1, lm, c) - OUTP(kp, lm, c))) * 2.0f;
+                                    if (fu) gIx = (float)(abs(OUT_AT(x + bside, c) - OUT_AT(x, c)) + abs(OUT_AT(x, c) - OUT_AT(x - bside, c)));
+                                    else gIx = (float)(abs(OUT_AT(x + bside, c) - OUT_AT(x, c))) * 2.0f;
                                 } else {
-                                    if (fu) gIx = (float)(abs(OUTP(kp, lm, c) - OUTP(km - 1, lm, c))) * 2.0f;
+                                    if (fu) gIx = (float)(abs(OUT_AT(x, c) - OUT_AT(x - bside, c))) * 2.0f;
                                     else gIx = 0;
                                 }
                                 if (fr) {
-                                    if (fl) gIy = (float)(abs(OUTP(km, lp + 1, c) - OUTP(km, lm, c)) + abs(OUTP(km, lm, c) - OUTP(km, lm - 1, c)));
-                                    else gIy = (float)(abs(OUTP(km, lp + 1, c) - OUTP(km, lm, c))) * 2.0f;
+                                    if (fl) gIy = (float)(abs(OUT_AT(x + 1, c) - OUT_AT(x, c)) + abs(OUT_AT(x, c) - OUT_AT(x - 1, c)));
+                                    else gIy = (float)(abs(OUT_AT(x + 1, c) - OUT_AT(x, c))) * 2.0f;
                                 } else {
-                                    if (fl) gIy = (float)(abs(OUTP(km, lm, c) - OUTP(km, lm - 1, c))) * 2.0f;
+                                    if (fl) gIy = (float)(abs(OUT_AT(x, c) - OUT_AT(x - 1, c))) * 2.0f;
                                     else gIy = 0;
                                 }
                                 gIx = -gIx;
@@ -658,15 +716,86 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __re
                                 if (fabs(dir) <= 0.01) dir = 0.000001f;
                                 else dir = fabsf((rx * gIx + ry * gIy) / sqrtf(vl * (gIx * gIx + gIy * gIy)));
                                 float w = dst * dir;
-                                term[c * 2 + 0] = w * (float)OUTP(k - 1, l - 1, c);
+                                term[c * 2 + 0] = w * (float)OUT_AT(x, c);
                                 term[c * 2 + 1] = w;
                             }
                         }
                     }
                 }
+            } else {
+                const int tp = u * 32 + lane;
+                if (tp < ntaps) {
+                    const int k = i - range + tp / side, l = j - range + tp % side;
+                    if (k > 0 && l > 0 && k < er - 1 && l < ec - 1) {
+                        if (known(k, l) && (l - j) * (l - j) + (k - i) * (k - i) <= range * range) {
+                            valid = true;
+                            const int km = k - 1 + (k == 1), kp = k - 1 - (k == er - 2);
+                            const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ec - 2);
+                            const bool fr = known(k, l + 1), fl = known(k, l - 1), fd = known(k + 1, l), fu = known(k - 1, l);
+                            if (METHOD == OFXCV_INPAINT_TELEA) {
+                                float ry = (float)(i - k), rx = (float)(j - l);
+                                float vl = rx * rx + ry * ry;
+                                float dst = (float)(1. / (vl * sqrt((double)vl)));
+                                float lev = (float)(1. / (1 + (double)fabsf(TV(k, l) - ti)));  // f32 difference, f64 sum (C fabs)
+                                float dir = rx * gTx + ry * gTy;
+                                if (fabs(dir) <= 0.01) dir = 0.000001f;
+                                float w = (float)fabs(dst * lev * dir);
+#pragma unroll
+                                for (int c = 0; c < CN; c++) {
+                                    float gIx, gIy;
+                                    if (fr) {
+                                        if (fl) gIx = (float)(OUTP(km, lp + 1, c) - OUTP(km, lm - 1, c)) * 2.0f;
+                                        else gIx = (float)(OUTP(km, lp + 1, c) - OUTP(km, lm, c));
+                                    } else {
+                                        if (fl) gIx = (float)(OUTP(km, lp, c) - OUTP(km, lm - 1, c));
+                                        else gIx = 0;
+                                    }
+                                    if (fd) {
+                                        if (fu) gIy = (float)(OUTP(kp + 1, lm, c) - OUTP(km - 1, lm, c)) * 2.0f;
+                                        else gIy = (float)(OUTP(kp + 1, lm, c) - OUTP(km, lm, c));
+                                    } else {
+                                        if (fu) gIy = (float)(OUTP(kp, lm, c) - OUTP(km - 1, lm, c));
+                                        else gIy = 0;
+                                    }
+                                    term[c * 4 + 0] = w * (float)OUTP(k - 1, l - 1, c);
+                                    term[c * 4 + 1] = -(w * (gIx * rx));
+                                    term[c * 4 + 2] = -(w * (gIy * ry));
+                                    term[c * 4 + 3] = w;
+                                }
+                            } else {
+                                float ry = (float)(k - i), rx = (float)(l - j);
+                                float vl = rx * rx + ry * ry;
+                                float dst = 1 / (vl * vl + 1);
+#pragma unroll
+                                for (int c = 0; c < CN; c++) {
+                                    float gIx, gIy;
+                                    if (fd) {
+                                        if (fu) gIx = (float)(abs(OUTP(kp + 1, lm, c) - OUTP(kp, lm, c)) + abs(OUTP(kp, lm, c) - OUTP(km - 1, lm, c)));
+                                        else gIx = (float)(abs(OUTP(kp + 1, lm, c) - OUTP(kp, lm, c))) * 2.0f;
+                                    } else {
+                                        if (fu) gIx = (float)(abs(OUTP(kp, lm, c) - OUTP(km - 1, lm, c))) * 2.0f;
+                                        else gIx = 0;
+                                    }
+                                    if (fr) {
+                                        if (fl) gIy = (float)(abs(OUTP(km, lp + 1, c) - OUTP(km, lm, c)) + abs(OUTP(km, lm, c) - OUTP(km, lm - 1, c)));
+                                        else gIy = (float)(abs(OUTP(km, lp + 1, c) - OUTP(km, lm, c))) * 2.0f;
+                                    } else {
+                                        if (fl) gIy = (float)(abs(OUTP(km, lm, c) - OUTP(km, lm - 1, c))) * 2.0f;
+                                        else gIy = 0;
+                                    }
+                                    gIx = -gIx;
+                                    float dir = rx * gIx + ry * gIy;
+                                    if (fabs(dir) <= 0.01) dir = 0.000001f;
+                                    else dir = fabsf((rx * gIx + ry * gIy) / sqrtf(vl * (gIx * gIx + gIy * gIy)));
+                                    float w = dst * dir;
+                                    term[c * 2 + 0] = w * (float)OUTP(k - 1, l - 1, c);
+                                    term[c * 2 + 1] = w;
+                                }
+                            }
+                        }
+                    }
+                }
             }
-#undef OUTP
-#undef TV
             const unsigned vmask = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
             for (int a = 0; a < NACC; a++) s_term[lane][a] = valid ? term[a] : 0.f;
@@ -682,6 +811,10 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __re
             }
             __syncwarp();
         }
+#undef OUTP
+#undef TV
+#undef KNOWN_AT
+#undef OUT_AT
 
         // finish: lane c gathers its channel's accumulators
         uint8_t result = 0;
@@ -706,10 +839,60 @@ ip_fill2(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __re
             *o = result;
         }
         __syncwarp();
-        if (lane == 0) {  // release: the colour bytes stored by lanes 0..CN-1 (ordered by the barrier above) before the flag
-            asm volatile("st.release.gpu.global.u8 [%0], %1;" ::"l"(done + id), "r"(1u) : "memory");
+        if (!READYQ) {
+            if (lane == 0) {  // release: the colour bytes stored by lanes 0..CN-1 (ordered by the barrier above) before the flag
+                asm volatile("st.release.gpu.global.u8 [%0], %1;" ::"l"(done + id), "r"(1u) : "memory");
+            }
+        } else {
+            // notify: every later-filled hole pixel whose box contains this pixel loses one dependency; whoever takes the
+            // last one publishes it.  acq_rel read-modify-writes: the colour bytes stored above (ordered by the barrier) are
+            // visible to the warp that later acquires the queue slot.
+            for (int b = lane; b < nbox; b += 32) {
+                const int bk = b / bside, bl = b - bk * bside;
+                const int k = k0 + bk, l = l0 + bl;
+                if (k < 0 || l < 0 || k >= er || l >= ec) continue;
+                const int n = k * ec + l;
+                const int fq = __ldg(fidx + n);
+                if (fq > (int)tk && fq != 0x7fffffff) {
+                    int old;
+                    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(dep + fq), "r"(-1) : "memory");
+                    if (old == 1) {
+                        const unsigned slot = atomicAdd(rtail, 1u);
+                        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(rq + slot), "r"(n) : "memory");
+                    }
+                }
+            }
         }
     }
+}
+
+// dependency counts of the ready-queue fill: dep[tk] = number of earlier-filled hole pixels in the (2r+3)^2 box of the
+// pixel with fill index tk; pixels without any go straight into the ready queue
+// Also counts the pixels whose latest dependency is one of the 64 tickets right before them (`near`): when that is most
+// of the mask, the fill order lays the dependency chains out one after the other (lines, blobs) and in-order tickets
+// would serialise them.
+__global__ void __launch_bounds__(256) ip_deps(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __restrict__ fidx,
+                                               int32_t* __restrict__ dep, int32_t* __restrict__ rq, unsigned* __restrict__ rtail,
+                                               unsigned* __restrict__ near, int range, IpGeom g)
+{
+    const unsigned tk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tk >= nfill) return;
+    const int id = (int)order[tk];
+    const int i = id / g.ec, j = id - i * g.ec;
+    int count = 0, latest = -1;
+    for (int k = max(i - range - 1, 0); k <= min(i + range + 1, g.er - 1); k++)
+        for (int l = max(j - range - 1, 0); l <= min(j + range + 1, g.ec - 1); l++) {
+            const int f = fidx[k * g.ec + l];
+            if (f >= 0 && f < (int)tk) {
+                count++;
+                latest = max(latest, f);
+            }
+        }
+    dep[tk] = count;
+    if (count == 0) rq[atomicAdd(rtail, 1u)] = id;
+    const bool is_near = latest >= 0 && (int)tk - latest <= 64;
+    const unsigned nb = __ballot_sync(__activemask(), is_near);
+    if (is_near && (threadIdx.x & 31) == (unsigned)(__ffs(nb) - 1)) atomicAdd(near, (unsigned)__popc(nb));
 }
 
 struct IpCounters {
@@ -852,15 +1035,42 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
             ip_fill_index<<<nblk, 256, 0, s>>>(hole, cnt, (uint32_t)g.np, fidx, g);
             OFXCV_LAUNCH_CHECK(ctx);
         }
+        // scheduler: dependency counters + ready queue when the fill order lays the dependency chains out one after the
+        // other (most pixels depend on one of the 64 tickets right before them), in-order tickets + flag spinning otherwise
+        // (cheaper per chain step; what an iid mask wants).  OFXCV_IP_READYQ=0/1 forces one.
+        int32_t* dep = (int32_t*)keys;  // the sort buffers are free once the march is over
+        int32_t* rq = dep + np;
+        bool ready_queue = false;
+        if (v2) {
+            OFXCV_CUDA(ctx, cudaMemsetAsync(rq, 0xff, (size_t)nfilled * 4, s));
+            OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->pending, 0, sizeof(unsigned), s));
+            OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->n_new, 0, sizeof(unsigned), s));
+            ip_deps<<<ofxcv_div_up((int)nfilled, 256), 256, 0, s>>>(order, nfilled, fidx, dep, rq, &ctr->pending, &ctr->n_new, range, g);
+            OFXCV_LAUNCH_CHECK(ctx);
+            OFXCV_CUDA(ctx, cudaMemcpyAsync(hctr, ctr, sizeof(IpCounters), cudaMemcpyDeviceToHost, s));
+            OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+            const char* rqenv = getenv("OFXCV_IP_READYQ");
+            ready_queue = rqenv ? *rqenv == '1' : (double)hctr->n_new > 0.7 * (double)nfilled;
+        }
         const int nbox_pad = ((2 * range + 3) * (2 * range + 3) + 3) & ~3;
         const size_t fill_smem = v2 ? ((size_t)nbox_pad * 8 + 32 * (IP_MAXACC + 1) * 4) * IP_WARPS : 0;
 #define IP_FILL(M, C)                                                                                                              \
     do {                                                                                                                           \
         if (v2) {                                                                                                                  \
-            if (fill_smem > 48 * 1024)                                                                                             \
-                OFXCV_CUDA(ctx, cudaFuncSetAttribute(ip_fill2<M, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem)); \
-            ip_fill2<M, C><<<blocks, IP_WARPS * 32, fill_smem, s>>>(order, nfilled, fidx, t, out, out_stride, done, &ctr->ticket,  \
-                                                                    range, g);                                                     \
+            if (fill_smem > 48 * 1024) {                                                                                           \
+                OFXCV_CUDA(ctx, cudaFuncSetAttribute(ip_fill_staged<M, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                                     (int)fill_smem));                                                             \
+                OFXCV_CUDA(ctx, cudaFuncSetAttribute(ip_fill_staged<M, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                                     (int)fill_smem));                                                             \
+            }                                                                                                                      \
+            if (ready_queue)                                                                                                       \
+                ip_fill_staged<M, C, true><<<blocks, IP_WARPS * 32, fill_smem, s>>>(order, nfilled, fidx, t, out, out_stride,     \
+                                                                                    done, dep, rq, &ctr->ticket, &ctr->pending,   \
+                                                                                    range, g);                                     \
+            else                                                                                                                   \
+                ip_fill_staged<M, C, false><<<blocks, IP_WARPS * 32, fill_smem, s>>>(order, nfilled, fidx, t, out, out_stride,    \
+                                                                                     done, dep, rq, &ctr->ticket, &ctr->pending,  \
+                                                                                     range, g);                                    \
         } else {                                                                                                                   \
             ip_fill<M, C><<<blocks, IP_WARPS * 32, 0, s>>>(order, nfilled, (uint32_t)g.np, hole, cnt, t, out, out_stride, done,    \
                                                            &ctr->ticket, range, g);                                                \
