@@ -98,3 +98,23 @@ def test_inpaint_1080p_ns_10pct(ctx, oracle, synth):
     got = ctx.inpaint(img, mask, 3, NS)
     ref = oracle.inpaint(img, mask, 3, NS)
     assert int((got != ref).sum()) == 0
+
+
+@pytest.mark.parametrize("sched", ["0", "1"])
+@pytest.mark.parametrize("method", [TELEA, NS])
+def test_inpaint_both_schedulers(ctx, oracle, synth, method, sched, monkeypatch):
+    """The fill kernel's two schedulers (in-order tickets + flag spinning / dependency counters + ready queue) must give
+    the same bytes on every kind of mask; the library picks one by itself, OFXCV_IP_READYQ forces it."""
+    monkeypatch.setenv("OFXCV_IP_READYQ", sched)
+    h, w = 96, 160
+    img = synth.texture(h, w, 6)
+    masks = _masks(synth, h, w)
+    lines = np.zeros((h, w), np.uint8)
+    lines[8:90:9, 5:150] = 255                     # scratches: every line is one long dependency chain
+    lines[20:70, 77] = 255
+    masks["lines"] = lines
+    for name, mask in masks.items():
+        for radius in (3, 6):
+            got = ctx.inpaint(img, mask, radius, method)
+            ref = oracle.inpaint(img, mask, radius, method)
+            assert np.array_equal(got, ref), "%s r=%d scheduler %s: %d differing bytes" % (name, radius, sched, int((got != ref).sum()))
