@@ -73,6 +73,10 @@ OFXCV_API void* ofxcv_device_alloc(ofxcv_ctx* ctx, size_t bytes);
 OFXCV_API void ofxcv_device_free(ofxcv_ctx* ctx, void* dptr);
 OFXCV_API void* ofxcv_pinned_alloc(ofxcv_ctx* ctx, size_t bytes);
 OFXCV_API void ofxcv_pinned_free(ofxcv_ctx* ctx, void* hptr);
+/* grow-only scratch owned by the context (freed by ofxcv_destroy), slot 0..7: what the OFX glue stages clips in, so that
+ * a render pays neither cudaMalloc nor cudaMallocHost (page-locking a 4K float RGBA frame takes tens of ms). */
+OFXCV_API void* ofxcv_scratch_device(ofxcv_ctx* ctx, int slot, size_t bytes);
+OFXCV_API void* ofxcv_scratch_pinned(ofxcv_ctx* ctx, int slot, size_t bytes);
 OFXCV_API int ofxcv_upload(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, const void* src_host, size_t bytes);
 OFXCV_API int ofxcv_download(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_host, const void* src_dev, size_t bytes);
 OFXCV_API int ofxcv_device_copy(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, const void* src_dev, size_t bytes);

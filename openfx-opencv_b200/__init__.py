@@ -82,6 +82,8 @@ def lib():
         "ofxcv_device_free": (None, [vp, vp]),
         "ofxcv_pinned_alloc": (vp, [vp, sz]),
         "ofxcv_pinned_free": (None, [vp, vp]),
+        "ofxcv_scratch_device": (vp, [vp, i, sz]),
+        "ofxcv_scratch_pinned": (vp, [vp, i, sz]),
         "ofxcv_upload": (i, [vp, vp, vp, vp, sz]),
         "ofxcv_download": (i, [vp, vp, vp, vp, sz]),
         "ofxcv_device_copy": (i, [vp, vp, vp, vp, sz]),

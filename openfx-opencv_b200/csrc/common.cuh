@@ -39,9 +39,9 @@ struct ofxcv_ctx {
     std::string last_error;
     uint64_t launches = 0;
     // named device workspaces, grown on demand, reused between calls
-    ofxcv_buf ws[48];
+    ofxcv_buf ws[56];
     // pinned host staging for the *_host entry points
-    ofxcv_buf pin[4];
+    ofxcv_buf pin[12];  // 0-3 internal staging, 4-11 ofxcv_scratch_pinned
     // per-family kernel timing (bench.py roofline numerator): events recorded on the launching stream
     bool timing = false;
     std::vector<ofxcv_timed_launch> timed[3];
@@ -184,4 +184,4 @@ enum {
     WS_FB1_TOT,
     WS_COUNT
 };
-static_assert(WS_COUNT <= 48, "workspace slots");
+static_assert(WS_COUNT + 8 <= 56, "workspace slots (the last 8 are ofxcv_scratch_device)");

@@ -266,6 +266,20 @@ void* ofxcv_device_alloc(ofxcv_ctx* ctx, size_t bytes)
     return p;
 }
 
+void* ofxcv_scratch_device(ofxcv_ctx* ctx, int slot, size_t bytes)
+{
+    if (!ctx || slot < 0 || slot >= 8) return nullptr;
+    ofxcv_device_guard g(ctx->device);
+    return ofxcv_ws(ctx, WS_COUNT + slot, bytes ? bytes : 1);
+}
+
+void* ofxcv_scratch_pinned(ofxcv_ctx* ctx, int slot, size_t bytes)
+{
+    if (!ctx || slot < 0 || slot >= 8) return nullptr;
+    ofxcv_device_guard g(ctx->device);
+    return ofxcv_pin(ctx, 4 + slot, bytes ? bytes : 1);
+}
+
 void ofxcv_device_free(ofxcv_ctx* ctx, void* dptr)
 {
     if (!ctx || !dptr) return;

@@ -255,24 +255,22 @@ inline int param_int(const Host& h, OfxParamHandle p, OfxTime t)
 }
 
 // a device buffer owned through the C ABI
+// Staging buffers of a render: grow-only scratch slots of the leased context (no cudaMalloc / cudaMallocHost per render).
+// One slot per buffer of a render action; a context is used by one render at a time (ContextLease).
 struct DevBuf {
-    ofxcv_ctx* ctx;
     void* p;
-    DevBuf(ofxcv_ctx* c, size_t bytes) : ctx(c), p(ofxcv_device_alloc(c, bytes))
+    DevBuf(ofxcv_ctx* c, int slot, size_t bytes) : p(ofxcv_scratch_device(c, slot, bytes))
     {
         if (!p) throw StatusException{kOfxStatErrMemory};
     }
-    ~DevBuf() { ofxcv_device_free(ctx, p); }
     DevBuf(const DevBuf&) = delete;
 };
 struct PinBuf {
-    ofxcv_ctx* ctx;
     void* p;
-    PinBuf(ofxcv_ctx* c, size_t bytes) : ctx(c), p(ofxcv_pinned_alloc(c, bytes))
+    PinBuf(ofxcv_ctx* c, int slot, size_t bytes) : p(ofxcv_scratch_pinned(c, slot, bytes))
     {
         if (!p) throw StatusException{kOfxStatErrMemory};
     }
-    ~PinBuf() { ofxcv_pinned_free(ctx, p); }
     PinBuf(const PinBuf&) = delete;
 };
 

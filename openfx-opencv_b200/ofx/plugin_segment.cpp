@@ -110,8 +110,8 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
     ContextLease lease(gPool);
     ofxcv_ctx* ctx = lease.ctx;
     const size_t n = (size_t)W * H;
-    PinBuf stage(ctx, n * 4);
-    DevBuf d_rgba(ctx, n * 4), d_rgb(ctx, n * 3), d_mask(ctx, n), d_lab(ctx, n * 4);
+    PinBuf stage(ctx, 0, n * 4);
+    DevBuf d_rgba(ctx, 0, n * 4), d_rgb(ctx, 1, n * 3), d_mask(ctx, 2, n), d_lab(ctx, 3, n * 4);
     gather_rows(src.img, win, 4, (char*)stage.p);
     check_cv(ofxcv_upload(ctx, nullptr, d_rgba.p, stage.p, n * 4));
     check_cv(ofxcv_rgba8_to_rgb8_mask(ctx, nullptr, (const uint8_t*)d_rgba.p, (ptrdiff_t)W * 4, (uint8_t*)d_rgb.p, (ptrdiff_t)W * 3,

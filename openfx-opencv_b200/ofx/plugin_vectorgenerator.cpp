@@ -200,8 +200,8 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
 
     ContextLease lease(gPool);
     ofxcv_ctx* ctx = lease.ctx;
-    PinBuf stage(ctx, n * 16);
-    DevBuf d_float(ctx, n * 16), d_gray0(ctx, n), d_gray1(ctx, n), d_flow(ctx, n * 8), d_dst(ctx, dev ? 16 : n * 16);
+    PinBuf stage(ctx, 0, dev ? 16 : n * 16);
+    DevBuf d_float(ctx, 0, dev ? 16 : n * 16), d_gray0(ctx, 1, n), d_gray1(ctx, 2, n), d_flow(ctx, 3, n * 8), d_dst(ctx, 4, dev ? 16 : n * 16);
     float* out_dev = dev ? (float*)dst.img.pixel(win.x1, win.y1) : (float*)d_dst.p;
     const ptrdiff_t out_stride = dev ? dst.img.rowBytes : (ptrdiff_t)W * 16;
     stage_gray(ctx, ref.img, win, dev, stage, d_float, (uint8_t*)d_gray0.p);
