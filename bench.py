@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU; torchrun for N>1)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's OpenCV CPU path, rank 0 only
 
-A "step" = one pass of the hot path over one batch of synthetic 3840x2160 frame pairs per GPU (default 8 pairs,
+A "step" = one pass of the hot path over one batch of synthetic 3840x2160 frame pairs per GPU (default 16 pairs,
 default plugin parameters: levels 3, winsize 3, 15 iterations, polyN 5, sigma 1.1).  Frames of the sequence are
 sharded one block per GPU with no data-path collective (weak scaling: per-GPU work is fixed).
   value  = flow fields (frame pairs) per second, whole job, frames already resident in HBM, CUDA-event timed,
@@ -387,7 +387,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=W4K)
     ap.add_argument("--height", type=int, default=H4K)
-    ap.add_argument("--pairs", type=int, default=8, help="frame pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=16, help="frame pairs per GPU per step (one clip block of pairs+1 frames)")
     ap.add_argument("--ref-workers", type=int, default=64, help="cap on CPU worker processes of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-plugins", action="store_true", help="skip the inpaint / watershed lines")
