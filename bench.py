@@ -350,7 +350,7 @@ def bench_plugins(pkg, synth, ctx, W, H, with_cpu):
             ent["bytes_differing_from_cv2"] = int((got != ref).sum())
         out[name] = ent
     mk = synth.seed_markers(H, W, 256, 5)
-    for nf in (1, 256):
+    for nf in (1, 512):
         d_rgbs, d_mks = ctx.alloc(W * H * 3 * nf), ctx.alloc(W * H * 4 * nf)
         L = pkg.lib()
         L.ofxcv_upload(ctx.h, None, d_rgbs.ptr, img.ctypes.data, W * H * 3)
