@@ -5,6 +5,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -72,3 +73,36 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"^\s*(import|from)\s+oracle\b|libofxcv_oracle|oracle/", text, re.M):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_concurrent_contexts_are_independent(pkg, synth):
+    """kOfxImageEffectRenderFullySafe (VectorGenerator.cpp:108): render threads use separate contexts concurrently; every
+    thread must get the bits a lone context gives."""
+    import threading
+    prev, nxt = synth.flow_pair(270, 480, seed=3)
+    img = synth.texture(120, 160, 1)
+    mask = synth.iid_mask(120, 160, 2, 0.1)
+    mk = synth.seed_markers(120, 160, 9, 5)
+    with pkg.Context(0) as c:
+        ref = (c.farneback(prev, nxt), c.inpaint(img, mask, 3, pkg.INPAINT_TELEA), c.watershed(img, mk))
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            with pkg.Context(0) as c:
+                for _ in range(3):
+                    out = (c.farneback(prev, nxt), c.inpaint(img, mask, 3, pkg.INPAINT_TELEA), c.watershed(img, mk))
+                results[i] = out
+        except Exception as e:  # surfaced below
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(4):
+        for a, b in zip(results[i], ref):
+            assert np.array_equal(a, b)
