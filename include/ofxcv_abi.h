@@ -161,6 +161,10 @@ OFXCV_API int ofxcv_inpaint_u8_host(ofxcv_ctx* ctx, const uint8_t* img, ptrdiff_
                                     const uint8_t* mask, ptrdiff_t mask_stride, uint8_t* out, ptrdiff_t out_stride,
                                     int W, int H, double radius, int method);
 OFXCV_API size_t ofxcv_inpaint_workspace_bytes(int W, int H, int channels);
+/* The fill stage is a dataflow over a dependency chain thousands of pixels deep: one frame leaves most of the GPU idle.
+ * A sequence renderer runs several frames at once (one context + host thread each) and gives every context a share
+ * of the SMs: persistent fill CTAs per SM for this context, 1..8 (default 8 = the whole GPU for one frame). */
+OFXCV_API void ofxcv_inpaint_set_fill_blocks(ofxcv_ctx* ctx, int blocks_per_sm);
 /* statistics of the last inpaint call on ctx: [0]=hole pixels, [1]=marching batches (0.7-wide T windows popped
  * in parallel), [2]=T relaxation rounds over all batches, [3]=kernel launches of the call */
 OFXCV_API int ofxcv_inpaint_last_stats(const ofxcv_ctx* ctx, int64_t stats[4]);

@@ -105,6 +105,7 @@ def lib():
         "ofxcv_inpaint_u8": (i, [vp, vp, vp, pd, i, vp, pd, vp, pd, i, i, d, i]),
         "ofxcv_inpaint_u8_host": (i, [vp, vp, pd, i, vp, pd, vp, pd, i, i, d, i]),
         "ofxcv_inpaint_workspace_bytes": (sz, [i, i, i]),
+        "ofxcv_inpaint_set_fill_blocks": (None, [vp, i]),
         "ofxcv_inpaint_last_stats": (i, [vp, C.POINTER(C.c_int64)]),
         "ofxcv_inpaint_debug_maps": (i, [vp, i, i, vp, vp]),
         "ofxcv_watershed_u8c3": (i, [vp, vp, vp, pd, vp, pd, i, i]),
@@ -224,6 +225,9 @@ class Context:
         if st != OK:
             raise OfxcvError(st, where, self.last_error())
 
+    def device(self):
+        return int(lib().ofxcv_device(self.h))
+
     def synchronize(self):
         self._check(lib().ofxcv_synchronize(self.h), "ofxcv_synchronize")
 
@@ -299,6 +303,9 @@ class Context:
         st = lib().ofxcv_inpaint_u8_host(self.h, _hp(img), w * cn, cn, _hp(mask), w, _hp(out), w * cn, w, h, float(radius), int(method))
         self._check(st, "ofxcv_inpaint_u8_host")
         return out
+
+    def inpaint_set_fill_blocks(self, blocks_per_sm):
+        lib().ofxcv_inpaint_set_fill_blocks(self.h, int(blocks_per_sm))
 
     def inpaint_stats(self):
         s = (C.c_int64 * 4)()

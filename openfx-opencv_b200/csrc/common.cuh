@@ -64,6 +64,7 @@ struct ofxcv_ctx {
     cudaStream_t stream_up = nullptr, stream_down = nullptr, stream_lane[2] = {nullptr, nullptr};
     cudaEvent_t lane_done[2] = {nullptr, nullptr}, lane_start = nullptr;
     cudaEvent_t seq_ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int ip_fill_blocks_per_sm = 8;  // persistent CTAs of the inpaint fill kernel per SM (ofxcv_inpaint_set_fill_blocks)
     int64_t inpaint_stats[4] = {0, 0, 0, 0};
     int64_t watershed_stats[4] = {0, 0, 0, 0};
 };

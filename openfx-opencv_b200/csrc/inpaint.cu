@@ -1022,7 +1022,7 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
     // Stage B
     if (nfilled > 0) {
         OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->ticket, 0, sizeof(unsigned), s));
-        int blocks = ctx->num_sms * 8;
+        int blocks = ctx->num_sms * ctx->ip_fill_blocks_per_sm;
         int need = ofxcv_div_up((int)nfilled, IP_WARPS);
         if (blocks > need) blocks = need;
         ofxcv_prof_scope ps(ctx, s, "ip_fill", 0);
@@ -1091,6 +1091,11 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
     ctx->inpaint_stats[2] = rounds_total;
     ctx->inpaint_stats[3] = (int64_t)(ctx->launches - launches0);
     return OFXCV_OK;
+}
+
+void ofxcv_inpaint_set_fill_blocks(ofxcv_ctx* ctx, int blocks_per_sm)
+{
+    if (ctx) ctx->ip_fill_blocks_per_sm = blocks_per_sm < 1 ? 1 : blocks_per_sm > 8 ? 8 : blocks_per_sm;
 }
 
 int ofxcv_inpaint_debug_maps(ofxcv_ctx* ctx, int W, int H, float* t_host, int32_t* order_host)
