@@ -474,7 +474,7 @@ constexpr int IP2_NPOS = 4;  // box positions per lane kept in flight / tabulate
 constexpr int IP2_NTAP = 3;  // taps per lane tabulated (covers r <= 4: 81 taps)
 
 template <int METHOD, int CN, bool READYQ>
-__global__ void __launch_bounds__(IP_WARPS * 32)
+__global__ void __launch_bounds__(IP_WARPS * 32, READYQ ? 2 : 4)  // in-order tickets: the resident-warp count is the window over the chains
 ip_fill_staged(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __restrict__ fidx, const float* __restrict__ t,
                uint8_t* out, ptrdiff_t ostride, uint8_t* done, int32_t* dep, int32_t* rq, unsigned* __restrict__ ticket,
                unsigned* __restrict__ rtail, int range, IpGeom g)
