@@ -59,3 +59,31 @@ def run_sharded(n_units, process_unit, world=None, rank=None):
     for part in gather_results(mine):
         merged.update(dict(part))
     return [merged[i] for i in range(n_units)]
+
+
+def flow_clip(ctx, load_frame, n_frames, params=None, world=None, rank=None, keep=True):
+    """Forward flow t -> t+1 of a whole clip, frame-sharded over the ranks of the default process group.
+
+    load_frame(t) -> HxW uint8 (host) is called only for the frames this rank needs (its contiguous block of outputs
+    plus the one-frame halo).  The rank's block goes through ONE clip call of the C ABI (ofxcv_farneback_sequence_u8_host:
+    one pyramid per frame, two pairs in flight, copies overlapped).  Returns (first, flows or None, checksums) where
+    `checksums` are the 64-bit checksums of ALL n_frames-1 flow fields in clip order, gathered from every rank (the
+    only collective on this path, besides the barriers)."""
+    import torch.distributed as dist
+    inited = dist.is_available() and dist.is_initialized()
+    world = world if world is not None else (dist.get_world_size() if inited else 1)
+    rank = rank if rank is not None else (dist.get_rank() if inited else 0)
+    first, count = shard_range(n_frames - 1, world, rank)
+    flows = []
+    if count > 0:
+        frames = [np.ascontiguousarray(load_frame(t), np.uint8) for t in frames_needed(first, count, n_frames)]
+        if inited:
+            dist.barrier()
+        flows = ctx.farneback_sequence(frames, params)
+    elif inited:
+        dist.barrier()
+    mine = [(first + i, checksum64(f)) for i, f in enumerate(flows)]
+    merged = {}
+    for part in gather_results(mine):
+        merged.update(dict(part))
+    return first, (flows if keep else None), [merged[i] for i in range(n_frames - 1)]

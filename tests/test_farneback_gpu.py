@@ -164,3 +164,23 @@ def test_farneback_4k_properties(ctx, pkg, synth):
     assert epe.mean() < 0.5 and np.median(epe) < 0.3, (epe.mean(), np.median(epe))   # u8 texture, polyN 5: ~0.2 px
     seq = ctx.farneback_sequence(f)
     assert np.array_equal(seq[0], a) and np.array_equal(seq[1], ctx.farneback(f[1], f[2]))
+
+
+def test_flow_clip_driver_single_rank(ctx, pkg, synth):
+    """sequence.flow_clip (the multi-GPU clip driver) on one rank: loads each frame once, equals the pairwise call."""
+    import importlib
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    h, w, n = 90, 120, 4
+    base = synth.gray(synth.texture(h, w, seed=31))
+    loaded = []
+
+    def load(t):
+        loaded.append(t)
+        return synth.shift_bilinear(base, 1.0 * t, 0.5 * t)
+
+    p = pkg.FbParams(levels=1, iterations=3)
+    first, flows, sums = seq.flow_clip(ctx, load, n, p)
+    assert first == 0 and loaded == [0, 1, 2, 3] and len(flows) == n - 1
+    for t in range(n - 1):
+        ref = ctx.farneback(synth.shift_bilinear(base, 1.0 * t, 0.5 * t), synth.shift_bilinear(base, 1.0 * (t + 1), 0.5 * (t + 1)), p)
+        assert np.array_equal(flows[t], ref) and sums[t] == seq.checksum64(ref)

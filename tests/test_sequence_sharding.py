@@ -65,3 +65,46 @@ def test_run_sharded_gloo_world2():
         owners = [o for o, _ in res]
         assert owners == [0, 0, 0, 0, 1, 1, 1]        # contiguous blocks
         assert tmax == 2.0
+
+
+class _FakeCtx:
+    """Stands in for the CUDA context: 'flow' of a pair = difference of the two frames (host logic under test is the
+    sharding, the halo and the gather)."""
+    def farneback_sequence(self, frames, params=None):
+        return [np.stack([b.astype(np.float32) - a, a.astype(np.float32)], axis=-1) for a, b in zip(frames[:-1], frames[1:])]
+
+
+def _clip_worker(rank, world, port, n_frames, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    loaded = []
+
+    def load(t):
+        loaded.append(t)
+        return np.full((4, 6), 3 * t, np.uint8)
+
+    first, flows, sums = seq.flow_clip(_FakeCtx(), load, n_frames)
+    q.put((rank, first, loaded, len(flows), sums))
+    dist.destroy_process_group()
+
+
+def test_flow_clip_gloo_world2():
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_frames, world, port = 8, 2, 29617 + os.getpid() % 1000
+    procs = [ctx.Process(target=_clip_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=100) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [seq.checksum64(np.stack([np.full((4, 6), 3.0, np.float32), np.full((4, 6), 3.0 * t, np.float32)], axis=-1)) for t in range(n_frames - 1)]
+    (r0, f0, l0, n0, s0), (r1, f1, l1, n1, s1) = outs
+    assert (f0, n0, l0) == (0, 4, [0, 1, 2, 3, 4])          # 7 pairs: rank 0 owns 4 of them + the halo frame
+    assert (f1, n1, l1) == (4, 3, [4, 5, 6, 7])
+    assert s0 == expect and s1 == expect                    # every rank sees every checksum, in clip order
