@@ -133,7 +133,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    args.out.emit(json.dumps(line))
     return 0
 
 
@@ -318,7 +318,7 @@ def run_ours(args):
                 line["plugins"] = bench_plugins(pkg, synth, ctx, W, H, not args.no_cpu)
             except Exception as e:
                 line["plugins"] = {"error": repr(e)}
-        print(json.dumps(line))
+        args.out.emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -424,6 +424,20 @@ def bench_plugins(pkg, synth, ctx, W, H, with_cpu):
     return out
 
 
+class OneLineStdout:
+    """Everything libraries write to fd 1 while the bench runs (NCCL prints its version there) goes to stderr; the JSON
+    line is written to the real stdout at the end, so that stdout carries exactly one line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text.rstrip("\n") + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -437,6 +451,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-plugins", action="store_true", help="skip the inpaint / watershed lines")
     args = ap.parse_args()
+    args.out = OneLineStdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
