@@ -441,6 +441,16 @@ class Context:
         self._check(lib().ofxcv_rgb8_to_rgba8(self.h, None, src.ptr, w * 3, dst.ptr, w * 4, w, h), "ofxcv_rgb8_to_rgba8")
         return dst.download((h, w, 4), np.uint8)
 
+    def rgb8_to_rgba8_noise(self, rgb, mask, noise_div, seed):
+        """RGB -> RGBA with the inpaint plugin's optional noise on hole pixels whose x is a multiple of 4."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        h, w = rgb.shape[:2]
+        src, m, dst = self.to_device(rgb), self.to_device(mask), self.alloc(w * h * 4)
+        self._check(lib().ofxcv_rgb8_to_rgba8_noise(self.h, None, src.ptr, w * 3, m.ptr, w, dst.ptr, w * 4, w, h, int(noise_div), int(seed)),
+                    "ofxcv_rgb8_to_rgba8_noise")
+        return dst.download((h, w, 4), np.uint8)
+
     def seed_grid(self, w, h, gx, gy, half):
         dst = self.alloc(w * h * 4)
         self._check(lib().ofxcv_seed_grid(self.h, None, dst.ptr, w * 4, w, h, gx, gy, half), "ofxcv_seed_grid")

@@ -38,6 +38,8 @@ int float_to_ff01(float value)
     return (int)(value * 0xff00 + 0.5);  // float product, double add, truncation (as the reference's template)
 }
 
+inline bool cv_aligned(const void* p, ptrdiff_t stride, int a) { return ((uintptr_t)p % a) == 0 && (stride % a) == 0; }
+
 std::once_flag g_lut_once;
 uint16_t g_lut[0x10000];
 float g_from_lut[256];  // byte -> linear float (Lut::fromFunc_uint8_to_float, ofxsLut.h:183-189)
@@ -82,6 +84,69 @@ __global__ void __launch_bounds__(256) cv_luma_srgb8(const char* __restrict__ sr
     }
     unsigned hi = __float_as_uint(l) >> 16;
     dst[(size_t)y * dst_stride + x] = (uint8_t)((lut[hi] + 0x80) >> 8);
+}
+
+// RGBA fast path of cv_luma_srgb8: a warp covers 128 pixels of a row, every lane loads pixels lane+32k (coalesced 16-byte loads,
+// four independent table gathers in flight) and the bytes are transposed through shuffles so that lane L stores pixels
+// 4L..4L+3 as one word (W % 4 == 0, dst rows 4-byte aligned, src rows 16-byte aligned)
+__global__ void __launch_bounds__(256) cv_luma_srgb8_rgba4(const char* __restrict__ src, ptrdiff_t src_stride, uint8_t* __restrict__ dst,
+                                                           ptrdiff_t dst_stride, int W, int H, const uint16_t* __restrict__ lut)
+{
+    const int lane = threadIdx.x & 31;
+    const int x0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 128;
+    const int y = blockIdx.y;
+    if (x0 >= W) return;
+    const float4* row = reinterpret_cast<const float4*>(src + (ptrdiff_t)y * src_stride);
+    float4 p[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) p[k] = x0 + lane + 32 * k < W ? row[x0 + lane + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float l = (float)__dadd_rn(__dadd_rn(__dmul_rn(0.2126, (double)p[k].x), __dmul_rn(0.7152, (double)p[k].y)),
+                                         __dmul_rn(0.0722, (double)p[k].z));
+        w |= (uint32_t)((lut[__float_as_uint(l) >> 16] + 0x80) >> 8) << (8 * k);
+    }
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) o |= ((__shfl_sync(0xffffffffu, w, (4 * lane + j) & 31) >> (8 * (lane >> 3))) & 0xffu) << (8 * j);
+    if (x0 + 4 * lane < W) reinterpret_cast<uint32_t*>(dst + (size_t)y * dst_stride)[(x0 >> 2) + lane] = o;
+}
+
+// RGBA -> RGBA fast paths of the two packed conversions: 4 pixels per thread, 256 apart (coalesced, 12 gathers in flight)
+__global__ void __launch_bounds__(256) cv_to_byte_packed44(const char* __restrict__ src, ptrdiff_t src_stride, uint8_t* __restrict__ dst,
+                                                           ptrdiff_t dst_stride, int W, int H, const uint16_t* __restrict__ lut)
+{
+    const int x0 = blockIdx.x * 1024 + threadIdx.x;
+    const int y = blockIdx.y;
+    const float4* row = reinterpret_cast<const float4*>(src + (ptrdiff_t)y * src_stride);
+    uchar4* out = reinterpret_cast<uchar4*>(dst + (size_t)y * dst_stride);
+    float4 p[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) p[k] = x0 + 256 * k < W ? row[x0 + 256 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uchar4 t;
+        t.x = (uint8_t)((lut[__float_as_uint(p[k].x) >> 16] + 0x80) >> 8);
+        t.y = (uint8_t)((lut[__float_as_uint(p[k].y) >> 16] + 0x80) >> 8);
+        t.z = (uint8_t)((lut[__float_as_uint(p[k].z) >> 16] + 0x80) >> 8);
+        t.w = alpha_to_byte(p[k].w);
+        if (x0 + 256 * k < W) out[x0 + 256 * k] = t;
+    }
+}
+__global__ void __launch_bounds__(256) cv_from_byte_packed44(const uint8_t* __restrict__ src, ptrdiff_t src_stride, char* __restrict__ dst,
+                                                             ptrdiff_t dst_stride, int W, int H, const float* __restrict__ from)
+{
+    const int x0 = blockIdx.x * 1024 + threadIdx.x;
+    const int y = blockIdx.y;
+    const uchar4* row = reinterpret_cast<const uchar4*>(src + (size_t)y * src_stride);
+    float4* out = reinterpret_cast<float4*>(dst + (ptrdiff_t)y * dst_stride);
+    uchar4 p[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) p[k] = x0 + 256 * k < W ? row[x0 + 256 * k] : make_uchar4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (x0 + 256 * k < W) out[x0 + 256 * k] = make_float4(from[p[k].x], from[p[k].y], from[p[k].z], (float)p[k].w / 255.f);
 }
 
 // Lut::to_byte_packed_nodither (ofxsLut.h:389-444) over whole rows: colour channels through the hipart table,
@@ -156,6 +221,82 @@ __global__ void __launch_bounds__(256) cv_rgba_split(const uint8_t* __restrict__
     q[0] = (uint8_t)r; q[1] = (uint8_t)g; q[2] = (uint8_t)b;
     int gray = (9798 * r + 19235 * g + 3735 * b + 16384) >> 15;
     mask[(size_t)y * mask_stride + x] = gray == 0 ? 255 : 0;
+}
+
+// 4 pixels per thread: one 16-byte RGBA load, three 4-byte RGB stores, one 4-byte mask store (rows 4-byte aligned, W % 4 == 0)
+__global__ void __launch_bounds__(256) cv_rgba_split4(const uint8_t* __restrict__ rgba, ptrdiff_t rgba_stride,
+                                                      uint8_t* __restrict__ rgb, ptrdiff_t rgb_stride,
+                                                      uint8_t* __restrict__ mask, ptrdiff_t mask_stride, int W4, int H)
+{
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x4 >= W4) return;
+    const uint4 p = reinterpret_cast<const uint4*>(rgba + (size_t)y * rgba_stride)[x4];
+    const uint32_t px[4] = {p.x, p.y, p.z, p.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int r = px[j] & 0xff, g = (px[j] >> 8) & 0xff, b = (px[j] >> 16) & 0xff;
+        const int gray = (9798 * r + 19235 * g + 3735 * b + 16384) >> 15;
+        m |= (gray == 0 ? 255u : 0u) << (8 * j);
+    }
+    // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+    uint32_t* q = reinterpret_cast<uint32_t*>(rgb + (size_t)y * rgb_stride) + 3 * (size_t)x4;
+    q[0] = (px[0] & 0xffffffu) | (px[1] << 24);
+    q[1] = ((px[1] >> 8) & 0xffffu) | (px[2] << 16);
+    q[2] = ((px[2] >> 16) & 0xffu) | (px[3] << 8);
+    reinterpret_cast<uint32_t*>(mask + (size_t)y * mask_stride)[x4] = m;
+}
+
+// 4 pixels per thread, bytes as lanes of 32-bit words (rows 4-byte aligned, W % 4 == 0, n <= 4)
+__global__ void __launch_bounds__(256) cv_dilate_rows4(const uint8_t* __restrict__ in, ptrdiff_t is, uint8_t* __restrict__ out,
+                                                       ptrdiff_t os, int W4, int H, int n)
+{
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x4 >= W4) return;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(in + (size_t)y * is);
+    const uint32_t w0 = x4 > 0 ? row[x4 - 1] : 0u, w1 = row[x4], w2 = x4 + 1 < W4 ? row[x4 + 1] : 0u;  // outside = not set
+    uint32_t v = w1;
+    for (int l = 1; l <= n; l++) {
+        v |= __funnelshift_r(w1, w2, 8 * l);       // bytes x+l
+        v |= __funnelshift_r(w0, w1, 32 - 8 * l);  // bytes x-l
+    }
+    reinterpret_cast<uint32_t*>(out + (size_t)y * os)[x4] = v;
+}
+__global__ void __launch_bounds__(256) cv_dilate_cols4(const uint8_t* __restrict__ in, ptrdiff_t is, uint8_t* __restrict__ out,
+                                                       ptrdiff_t os, int W4, int H, int n)
+{
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x4 >= W4) return;
+    uint32_t v = 0;
+    for (int k = max(y - n, 0); k <= min(y + n, H - 1); k++) v |= reinterpret_cast<const uint32_t*>(in + (size_t)k * is)[x4];
+    reinterpret_cast<uint32_t*>(out + (size_t)y * os)[x4] = v;
+}
+
+// 4 pixels per thread: three 4-byte RGB loads, one 16-byte RGBA store, optional noise (same rule as cv_rgb_to_rgba_noise)
+__device__ __forceinline__ unsigned cv_hash(unsigned x, unsigned y, unsigned s);
+__global__ void __launch_bounds__(256) cv_rgb_to_rgba4(const uint8_t* __restrict__ rgb, ptrdiff_t rgb_stride,
+                                                       const uint8_t* __restrict__ mask, ptrdiff_t mask_stride,
+                                                       uint8_t* __restrict__ rgba, ptrdiff_t rgba_stride, int W4, int H, int noise_div,
+                                                       unsigned seed)
+{
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x4 >= W4) return;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(rgb + (size_t)y * rgb_stride) + 3 * (size_t)x4;
+    const uint32_t a = p[0], b = p[1], c = p[2];
+    uint32_t px[4] = {a & 0xffffffu, (a >> 24) | ((b & 0xffffu) << 8), (b >> 16) | ((c & 0xffu) << 16), c >> 8};
+    if (noise_div > 0 && mask[(size_t)y * mask_stride + 4 * (size_t)x4]) {  // only pixels whose x is a multiple of 4 get noise
+        const int d = ((int)(cv_hash(4u * x4, y, seed) % 10u) - 5) / noise_div;
+        uint32_t o = 0;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) o |= (uint32_t)min(max((int)((px[0] >> (8 * ch)) & 0xff) + d, 0), 255) << (8 * ch);
+        px[0] = o;
+    }
+    reinterpret_cast<uint4*>(rgba + (size_t)y * rgba_stride)[x4] =
+        make_uint4(px[0] | 0xff000000u, px[1] | 0xff000000u, px[2] | 0xff000000u, px[3] | 0xff000000u);
 }
 
 // n successive 3x3 rect dilations == one (2n+1)^2 rect dilation (constant border = not set)
@@ -322,7 +463,10 @@ int ofxcv_rgba32f_to_srgb_gray8(ofxcv_ctx* ctx, ofxcv_stream stream, const float
     const float* from;
     int st = srgb_tables(ctx, s, &dl, &from);
     if (st < 0) return st;
-    cv_luma_srgb8<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>((const char*)src, src_stride, ncomp, dst, dst_stride, W, H, dl);
+    if (ncomp == 4 && (W & 3) == 0 && cv_aligned(dst, dst_stride, 4))
+        cv_luma_srgb8_rgba4<<<dim3(ofxcv_div_up(W, 1024), H), 256, 0, s>>>((const char*)src, src_stride, dst, dst_stride, W, H, dl);
+    else
+        cv_luma_srgb8<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>((const char*)src, src_stride, ncomp, dst, dst_stride, W, H, dl);
     OFXCV_LAUNCH_CHECK(ctx);
     return OFXCV_OK;
 }
@@ -340,7 +484,10 @@ int ofxcv_rgba32f_to_srgb8_packed(ofxcv_ctx* ctx, ofxcv_stream stream, const flo
     const float* from;
     int st = srgb_tables(ctx, s, &to, &from);
     if (st < 0) return st;
-    cv_to_byte_packed<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>((const char*)src, src_stride, src_ncomp, dst, dst_stride, dst_ncomp, W, H, to);
+    if (src_ncomp == 4 && dst_ncomp == 4 && cv_aligned(src, src_stride, 16) && cv_aligned(dst, dst_stride, 4))
+        cv_to_byte_packed44<<<dim3(ofxcv_div_up(W, 1024), H), 256, 0, s>>>((const char*)src, src_stride, dst, dst_stride, W, H, to);
+    else
+        cv_to_byte_packed<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>((const char*)src, src_stride, src_ncomp, dst, dst_stride, dst_ncomp, W, H, to);
     OFXCV_LAUNCH_CHECK(ctx);
     return OFXCV_OK;
 }
@@ -357,7 +504,10 @@ int ofxcv_srgb8_packed_to_rgba32f(ofxcv_ctx* ctx, ofxcv_stream stream, const uin
     const float* from;
     int st = srgb_tables(ctx, s, &to, &from);
     if (st < 0) return st;
-    cv_from_byte_packed<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>(src, src_stride, (char*)dst, dst_stride, ncomp, W, H, from);
+    if (ncomp == 4 && cv_aligned(src, src_stride, 4) && cv_aligned(dst, dst_stride, 16))
+        cv_from_byte_packed44<<<dim3(ofxcv_div_up(W, 1024), H), 256, 0, s>>>(src, src_stride, (char*)dst, dst_stride, W, H, from);
+    else
+        cv_from_byte_packed<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>(src, src_stride, (char*)dst, dst_stride, ncomp, W, H, from);
     OFXCV_LAUNCH_CHECK(ctx);
     return OFXCV_OK;
 }
@@ -383,14 +533,27 @@ int ofxcv_rgba8_to_rgb8_mask(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t*
     ofxcv_device_guard guard(ctx->device);
     cudaStream_t s = pick(ctx, stream);
     dim3 grid(ofxcv_div_up(W, 256), H);
-    cv_rgba_split<<<grid, 256, 0, s>>>(rgba, rgba_stride, rgb, rgb_stride, mask, mask_stride, W, H);
+    // 4-pixel kernels need W % 4 == 0 and rows that start on the natural boundary of the word they use
+    const bool w4 = (W & 3) == 0;
+    const bool mask4 = w4 && cv_aligned(mask, mask_stride, 4);
+    dim3 grid4(ofxcv_div_up(W / 4 > 0 ? W / 4 : 1, 256), H);
+    if (mask4 && cv_aligned(rgba, rgba_stride, 16) && cv_aligned(rgb, rgb_stride, 4))
+        cv_rgba_split4<<<grid4, 256, 0, s>>>(rgba, rgba_stride, rgb, rgb_stride, mask, mask_stride, W / 4, H);
+    else
+        cv_rgba_split<<<grid, 256, 0, s>>>(rgba, rgba_stride, rgb, rgb_stride, mask, mask_stride, W, H);
     OFXCV_LAUNCH_CHECK(ctx);
     if (dilate_iterations > 0) {
         uint8_t* tmp = (uint8_t*)ofxcv_ws(ctx, WS_MISC0, (size_t)W * H);
         if (!tmp) return OFXCV_ERR_MEMORY;
-        cv_dilate_rows<<<grid, 256, 0, s>>>(mask, mask_stride, tmp, W, W, H, dilate_iterations);
-        OFXCV_LAUNCH_CHECK(ctx);
-        cv_dilate_cols<<<grid, 256, 0, s>>>(tmp, W, mask, mask_stride, W, H, dilate_iterations);
+        if (mask4 && dilate_iterations <= 4) {
+            cv_dilate_rows4<<<grid4, 256, 0, s>>>(mask, mask_stride, tmp, W, W / 4, H, dilate_iterations);
+            OFXCV_LAUNCH_CHECK(ctx);
+            cv_dilate_cols4<<<grid4, 256, 0, s>>>(tmp, W, mask, mask_stride, W / 4, H, dilate_iterations);
+        } else {
+            cv_dilate_rows<<<grid, 256, 0, s>>>(mask, mask_stride, tmp, W, W, H, dilate_iterations);
+            OFXCV_LAUNCH_CHECK(ctx);
+            cv_dilate_cols<<<grid, 256, 0, s>>>(tmp, W, mask, mask_stride, W, H, dilate_iterations);
+        }
         OFXCV_LAUNCH_CHECK(ctx);
     }
     return OFXCV_OK;
@@ -402,7 +565,11 @@ int ofxcv_rgb8_to_rgba8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb,
     if (!ctx) return OFXCV_ERR_NO_DEVICE;
     if (!rgb || !rgba || W <= 0 || H <= 0) return OFXCV_ERR_BAD_ARG;
     ofxcv_device_guard guard(ctx->device);
-    cv_rgb_to_rgba<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, pick(ctx, stream)>>>(rgb, rgb_stride, rgba, rgba_stride, W, H);
+    if ((W & 3) == 0 && cv_aligned(rgb, rgb_stride, 4) && cv_aligned(rgba, rgba_stride, 16))
+        cv_rgb_to_rgba4<<<dim3(ofxcv_div_up(W / 4, 256), H), 256, 0, pick(ctx, stream)>>>(rgb, rgb_stride, nullptr, 0, rgba, rgba_stride,
+                                                                                         W / 4, H, 0, 0u);
+    else
+        cv_rgb_to_rgba<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, pick(ctx, stream)>>>(rgb, rgb_stride, rgba, rgba_stride, W, H);
     OFXCV_LAUNCH_CHECK(ctx);
     return OFXCV_OK;
 }
@@ -413,8 +580,12 @@ int ofxcv_rgb8_to_rgba8_noise(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t
     if (!ctx) return OFXCV_ERR_NO_DEVICE;
     if (!rgb || !rgba || W <= 0 || H <= 0 || (noise_div > 0 && !mask)) return OFXCV_ERR_BAD_ARG;
     ofxcv_device_guard guard(ctx->device);
-    cv_rgb_to_rgba_noise<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, pick(ctx, stream)>>>(rgb, rgb_stride, mask, mask_stride, rgba, rgba_stride,
-                                                                                       W, H, noise_div, seed);
+    if ((W & 3) == 0 && cv_aligned(rgb, rgb_stride, 4) && cv_aligned(rgba, rgba_stride, 16))
+        cv_rgb_to_rgba4<<<dim3(ofxcv_div_up(W / 4, 256), H), 256, 0, pick(ctx, stream)>>>(rgb, rgb_stride, mask, mask_stride, rgba,
+                                                                                         rgba_stride, W / 4, H, noise_div, seed);
+    else
+        cv_rgb_to_rgba_noise<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, pick(ctx, stream)>>>(rgb, rgb_stride, mask, mask_stride, rgba,
+                                                                                           rgba_stride, W, H, noise_div, seed);
     OFXCV_LAUNCH_CHECK(ctx);
     return OFXCV_OK;
 }

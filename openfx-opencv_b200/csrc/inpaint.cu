@@ -51,7 +51,9 @@ __global__ void __launch_bounds__(256) ip_init(const uint8_t* __restrict__ mask,
     cnt[id] = CNT_NONE;
     rnd[id] = 0;
     done[id] = 0;
-    if (h) atomicAdd(&counters[0], 1u);  // number of hole pixels
+    // number of hole pixels: one atomic per warp
+    const unsigned hb = __ballot_sync(__activemask(), h != 0);
+    if (h && (threadIdx.x & 31) == (unsigned)(__ffs(hb) - 1)) atomicAdd(&counters[0], (unsigned)__popc(hb));
 }
 
 // band = known interior pixels with a hole 4-neighbour; heap entries with T = 0 pushed in row-major order

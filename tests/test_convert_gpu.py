@@ -96,3 +96,51 @@ def test_packed_srgb_conversions(ctx, oracle):
     b = np.arange(256, dtype=np.uint8)
     lin = ctx.srgb8_packed_to_rgba32f(np.stack([b, b, b, b], axis=-1).reshape(1, 256, 4))
     assert np.array_equal(ctx.rgba32f_to_srgb8_packed(lin, 4)[0], np.stack([b, b, b, b], axis=-1))
+
+
+def _hash(x, y, s):
+    m = 0xFFFFFFFF
+    h = ((x * 0x9E3779B1) & m) ^ (((y + 0x7F4A7C15) & m) * 0x85EBCA77 & m) ^ (((s + 1) & m) * 0xC2B2AE3D & m)
+    h ^= h >> 15; h = h * 0x2C1B3C6D & m; h ^= h >> 12; h = h * 0x297A2D39 & m; h ^= h >> 15
+    return h
+
+
+@pytest.mark.parametrize("shape", [(9, 1284), (5, 132), (3, 4), (6, 1023)])
+def test_word_wide_staging_paths(ctx, oracle, synth, shape):
+    """Widths that are multiples of 4 take the 4-pixels-per-thread kernels (several warps and blocks per row, ragged
+    last warp); 1023 takes the byte kernels.  Both must give the numpy / oracle answer."""
+    h, w = shape
+    rng = np.random.default_rng(w)
+    img = (rng.random((h, w, 4), dtype=np.float32) * 1.3 - 0.15).astype(np.float32)
+    assert np.array_equal(ctx.rgba32f_to_srgb_gray8(img), oracle.luma_srgb_gray8(img))
+    assert np.array_equal(ctx.rgba32f_to_srgb8_packed(img, 4), oracle.to_byte_packed(img, 4))
+    codes = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    assert np.array_equal(ctx.srgb8_packed_to_rgba32f(codes), oracle.from_byte_packed(codes))
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    rgba[rng.random((h, w)) < 0.03, :3] = 0
+    rgba[0, 0, :3] = 0; rgba[h - 1, w - 1, :3] = 0          # holes in the corners: dilation meets the border
+    hole = synth.gray(rgba[..., :3]) == 0
+    for n in (0, 1, 3, 4, 5):                                 # 5 is beyond the word-wide dilation
+        rgb, mask = ctx.rgba8_to_rgb8_mask(rgba, n)
+        assert np.array_equal(rgb, rgba[..., :3])
+        ref = hole
+        if n:
+            pad = np.pad(hole, n)
+            ref = np.zeros_like(hole)
+            for dy in range(2 * n + 1):
+                for dx in range(2 * n + 1):
+                    ref |= pad[dy:dy + h, dx:dx + w]
+        assert np.array_equal(mask, ref.astype(np.uint8) * 255), n
+    rgb = np.ascontiguousarray(rgba[..., :3])
+    out = ctx.rgb8_to_rgba8(rgb)
+    assert np.array_equal(out[..., :3], rgb) and (out[..., 3] == 255).all()
+    m8 = hole.astype(np.uint8) * 255
+    for div in (0, 1, 2):
+        got = ctx.rgb8_to_rgba8_noise(rgb, m8, div, 77)
+        ref = np.concatenate([rgb, np.full((h, w, 1), 255, np.uint8)], axis=-1).astype(np.int64)
+        if div:
+            for y, x in zip(*np.nonzero(hole)):
+                if x % 4 == 0:
+                    d = int((_hash(int(x), int(y), 77) % 10 - 5) / div)   # C division truncates toward zero
+                    ref[y, x, :3] = np.clip(ref[y, x, :3] + d, 0, 255)
+        assert np.array_equal(got, ref.astype(np.uint8)), div
