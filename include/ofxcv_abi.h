@@ -147,6 +147,38 @@ OFXCV_API int ofxcv_farneback_sequence_u8_host(ofxcv_ctx* ctx, const uint8_t* co
                                                int H, int nframes, float* const* flows, ptrdiff_t flow_stride,
                                                const ofxcv_fb_params* params);
 
+/* ---- Dual TV-L1 optical flow (the plugin's second method) --------------------------------------------------- */
+/* Replaces createOptFlow_DualTVL1() + set{Tau,Lambda,Theta,ScalesNumber,WarpingsNumber,Epsilon,InnerIterations} +
+ * calc(prev, next, flow) as called at /root/reference/VectorGenerator/VectorGenerator.cpp:436-492 (parameter
+ * defaults :874-929, `iterations` :814).  The last three fields are the values OpenCV 3/4 fixes and the plugin never
+ * sets.  PARITY UNPINNED for the method as a whole (no OpenCV build with DualTVL1 is available to pin it): results
+ * are bit-identical to the CPU test oracle (tvl1.c), whose primitives (bicubic remap, 5x5 median, bilinear resize) are pinned to cv2. */
+typedef struct ofxcv_tvl1_params {
+    double tau;           /* 0.25 (VectorGenerator.cpp:877) */
+    double lambda;        /* 0.15 (:887) */
+    double theta;         /* 0.3  (:897) */
+    double epsilon;       /* 0.01 (:926) -- a warping stops once the squared flow update <= epsilon^2 * W * H */
+    int nscales;          /* 5    (:907) -- scales smaller than 16 px are dropped */
+    int warps;            /* 5    (:917) */
+    int iterations;       /* 15   (:814) -- inner iterations (setInnerIterations / setIterations, :481-485) */
+    int outer_iterations; /* 10   OpenCV default; one 5x5 median of the flow per outer iteration */
+    double scale_step;    /* 0.8  OpenCV default */
+    int median_filtering; /* 5    OpenCV default; <= 1 switches the median off, other sizes are rejected */
+} ofxcv_tvl1_params;
+
+OFXCV_API void ofxcv_tvl1_default_params(ofxcv_tvl1_params* p);
+OFXCV_API int ofxcv_tvl1_scales(int W, int H, const ofxcv_tvl1_params* p);
+OFXCV_API size_t ofxcv_tvl1_workspace_bytes(int W, int H, const ofxcv_tvl1_params* p);
+/* algorithmic bytes of ONE full-resolution inner iteration (two launches): 88 B per pixel
+ * (A 16 + U 8 in/8 out + P 16 read by the primal step; U 8 + P 16 in/16 out by the dual step). */
+OFXCV_API double ofxcv_tvl1_iter_bytes(int W, int H);
+/* prev/next: 8-bit gray, `stride` bytes per row; flow: interleaved (dx,dy) float32, `flow_stride` BYTES/row, rows
+ * 8-byte aligned.  Asynchronous on `stream` like ofxcv_farneback_u8; the convergence test stays on the device. */
+OFXCV_API int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, const uint8_t* next, ptrdiff_t stride,
+                            int W, int H, float* flow, ptrdiff_t flow_stride, const ofxcv_tvl1_params* params);
+/* inner iterations the last ofxcv_tvl1_u8 of this context actually ran (synchronises the device); -1 if none */
+OFXCV_API int64_t ofxcv_tvl1_iterations_run(ofxcv_ctx* ctx);
+
 /* ---- inpainting ------------------------------------------------------------------------------------- */
 /* Replaces cvInpaint(image0, mask, image1, radius, CV_INPAINT_TELEA) at
  * /root/reference/opencv2fx/inpaint/inpaint.cpp:311-318 (Telea hard-wired at :311; Navier-Stokes is the

@@ -42,6 +42,18 @@ class FbParams(C.Structure):
         super().__init__(pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags)
 
 
+class Tvl1Params(C.Structure):
+    """ofxcv_tvl1_params (defaults = the reference plugin's, VectorGenerator.cpp:814,:874-929, + OpenCV's fixed ones)."""
+    _fields_ = [("tau", C.c_double), ("lambda_", C.c_double), ("theta", C.c_double), ("epsilon", C.c_double),
+                ("nscales", C.c_int), ("warps", C.c_int), ("iterations", C.c_int), ("outer_iterations", C.c_int),
+                ("scale_step", C.c_double), ("median_filtering", C.c_int)]
+
+    def __init__(self, tau=0.25, lambda_=0.15, theta=0.3, epsilon=0.01, nscales=5, warps=5, iterations=15,
+                 outer_iterations=10, scale_step=0.8, median_filtering=5):
+        super().__init__(tau, lambda_, theta, epsilon, nscales, warps, iterations, outer_iterations, scale_step,
+                         median_filtering)
+
+
 def build(force=False):
     """Compile libofxcv_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
     import subprocess
@@ -63,6 +75,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, i, sz, pd, d = C.c_void_p, C.c_int, C.c_size_t, C.c_ssize_t, C.c_double
     fbp = C.POINTER(FbParams)
+    tvp = C.POINTER(Tvl1Params)
     sigs = {
         "ofxcv_abi_version": (i, []),
         "ofxcv_status_string": (C.c_char_p, [i]),
@@ -94,6 +107,12 @@ def lib():
         "ofxcv_farneback_iter_bytes": (d, [i, i, fbp]),
         "ofxcv_farneback_workspace_bytes": (sz, [i, i, fbp]),
         "ofxcv_farneback_u8": (i, [vp, vp, vp, vp, pd, i, i, vp, pd, fbp]),
+        "ofxcv_tvl1_default_params": (None, [tvp]),
+        "ofxcv_tvl1_scales": (i, [i, i, tvp]),
+        "ofxcv_tvl1_workspace_bytes": (sz, [i, i, tvp]),
+        "ofxcv_tvl1_iter_bytes": (d, [i, i]),
+        "ofxcv_tvl1_u8": (i, [vp, vp, vp, vp, pd, i, i, vp, pd, tvp]),
+        "ofxcv_tvl1_iterations_run": (C.c_int64, [vp]),
         "ofxcv_farneback_u8_host": (i, [vp, vp, vp, pd, i, i, vp, pd, fbp]),
         "ofxcv_farneback_u8_keyed": (i, [vp, vp, vp, vp, pd, i, i, vp, pd, fbp, C.c_uint64, C.c_uint64]),
         "ofxcv_content_key_u8": (i, [vp, vp, vp, pd, i, i, C.POINTER(C.c_uint64)]),
@@ -340,6 +359,23 @@ class Context:
         params = params or FbParams()
         st = lib().ofxcv_farneback_u8(self.h, stream, prev_d, next_d, stride or w, w, h, flow_d, flow_stride or w * 8, C.byref(params))
         self._check(st, "ofxcv_farneback_u8")
+
+    def tvl1_dev(self, prev_d, next_d, w, h, flow_d, params=None, stride=None, flow_stride=None, stream=None):
+        params = params or Tvl1Params()
+        st = lib().ofxcv_tvl1_u8(self.h, stream, prev_d, next_d, stride or w, w, h, flow_d, flow_stride or w * 8, C.byref(params))
+        self._check(st, "ofxcv_tvl1_u8")
+
+    def tvl1(self, prev, nxt, params=None):
+        """Dual TV-L1 flow prev -> nxt (HxW uint8, host).  Returns (HxWx2 float32 flow, inner iterations run)."""
+        prev = np.ascontiguousarray(prev, np.uint8)
+        nxt = np.ascontiguousarray(nxt, np.uint8)
+        if prev.ndim != 2 or prev.shape != nxt.shape:
+            raise ValueError("prev/next must be equal-shape HxW uint8")
+        h, w = prev.shape
+        a, b, f = self.to_device(prev), self.to_device(nxt), self.alloc(w * h * 8)
+        self.tvl1_dev(a.ptr, b.ptr, w, h, f.ptr, params)
+        flow = f.download((h, w, 2), np.float32)
+        return flow, int(lib().ofxcv_tvl1_iterations_run(self.h))
 
     def farneback_keyed_dev(self, prev_d, next_d, w, h, flow_d, key_prev, key_next, params=None, stream=None):
         params = params or FbParams()

@@ -65,6 +65,7 @@ struct ofxcv_ctx {
     cudaEvent_t lane_done[2] = {nullptr, nullptr}, lane_start = nullptr;
     cudaEvent_t seq_ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int ip_fill_blocks_per_sm = 8;  // persistent CTAs of the inpaint fill kernel per SM (ofxcv_inpaint_set_fill_blocks)
+    size_t tv_ctrl_off = 0;  // where the last ofxcv_tvl1_u8 put its control block inside WS_TV_ARENA
     int64_t inpaint_stats[4] = {0, 0, 0, 0};
     int64_t watershed_stats[4] = {0, 0, 0, 0};
 };
@@ -183,6 +184,7 @@ enum {
     WS_FB1_FLOWA,
     WS_FB1_FLOWB,
     WS_FB1_TOT,
+    WS_TV_ARENA,  // Dual TV-L1: pyramids + J/A/P/U planes + control block, one allocation
     WS_COUNT
 };
 static_assert(WS_COUNT + 8 <= 56, "workspace slots (the last 8 are ofxcv_scratch_device)");

@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(256) cv_dilate_rows4(const uint8_t* __restrict
     const uint32_t w0 = x4 > 0 ? row[x4 - 1] : 0u, w1 = row[x4], w2 = x4 + 1 < W4 ? row[x4 + 1] : 0u;  // outside = not set
     uint32_t v = w1;
     for (int l = 1; l <= n; l++) {
-        v |= __funnelshift_r(w1, w2, 8 * l);       // bytes x+l
-        v |= __funnelshift_r(w0, w1, 32 - 8 * l);  // bytes x-l
+        v |= __funnelshift_rc(w1, w2, 8 * l);      // bytes x+l (clamped shift: l = 4 gives w2)
+        v |= __funnelshift_rc(w0, w1, 32 - 8 * l); // bytes x-l
     }
     reinterpret_cast<uint32_t*>(out + (size_t)y * os)[x4] = v;
 }

@@ -42,18 +42,19 @@ __global__ void __launch_bounds__(256) ip_init(const uint8_t* __restrict__ mask,
                                                uint8_t* __restrict__ done, unsigned* __restrict__ counters, IpGeom g)
 {
     int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= g.np) return;
-    int i = id / g.ec, j = id - i * g.ec;
     uint8_t h = 0;
-    if (i >= 1 && i <= g.H && j >= 1 && j <= g.W) h = mask[(size_t)(i - 1) * mstride + (j - 1)] != 0;
-    hole[id] = h;
-    t[id] = T_FAR;
-    cnt[id] = CNT_NONE;
-    rnd[id] = 0;
-    done[id] = 0;
-    // number of hole pixels: one atomic per warp
-    const unsigned hb = __ballot_sync(__activemask(), h != 0);
-    if (h && (threadIdx.x & 31) == (unsigned)(__ffs(hb) - 1)) atomicAdd(&counters[0], (unsigned)__popc(hb));
+    if (id < g.np) {
+        int i = id / g.ec, j = id - i * g.ec;
+        if (i >= 1 && i <= g.H && j >= 1 && j <= g.W) h = mask[(size_t)(i - 1) * mstride + (j - 1)] != 0;
+        hole[id] = h;
+        t[id] = T_FAR;
+        cnt[id] = CNT_NONE;
+        rnd[id] = 0;
+        done[id] = 0;
+    }
+    // number of hole pixels: one atomic per block (same-address atomics run at ~2 per ns)
+    const int c = __syncthreads_count(h != 0);
+    if (threadIdx.x == 0 && c) atomicAdd(&counters[0], (unsigned)c);
 }
 
 // band = known interior pixels with a hole 4-neighbour; heap entries with T = 0 pushed in row-major order
@@ -120,8 +121,14 @@ __global__ void __launch_bounds__(256) ip_pass_a(uint8_t* __restrict__ st, const
         else if (s == ST_NEW) { st[id] = ST_HEAP; s = ST_HEAP; }
         if (s == ST_HEAP) local = __float_as_uint(t[id]);  // T >= 0: the bit pattern orders like the value
     }
+    __shared__ unsigned wmin[8];
     local = __reduce_min_sync(0xffffffffu, local);
-    if ((threadIdx.x & 31) == 0 && local != 0xffffffffu) atomicMin(tau_bits, local);
+    if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {  // one atomic per block
+        local = __reduce_min_sync(0xffffffffu, threadIdx.x < 8 ? wmin[threadIdx.x] : 0xffffffffu);
+        if (threadIdx.x == 0 && local != 0xffffffffu) atomicMin(tau_bits, local);
+    }
 }
 
 // pass B: select the window [tau, tau+0.7)
@@ -142,28 +149,43 @@ __global__ void __launch_bounds__(256) ip_pass_c(uint8_t* __restrict__ st, const
                                                  unsigned* __restrict__ n_new, IpGeom g)
 {
     int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= g.np) return;
-    if (st[id] != ST_INSIDE) return;
-    // neighbour p of q        q = p + dir[slot]
-    //  p above  (id-ec)       slot 2 (down)
-    //  p left   (id-1)        slot 3 (right)
-    //  p below  (id+ec)       slot 0 (up)
-    //  p right  (id+1)        slot 1 (left)
-    const int nb[4] = {id - g.ec, id - 1, id + g.ec, id + 1};
-    const unsigned slot[4] = {2u, 3u, 0u, 1u};
     unsigned long long best = ~0ull;
+    if (id < g.np && st[id] == ST_INSIDE) {
+        // neighbour p of q        q = p + dir[slot]
+        //  p above  (id-ec)       slot 2 (down)
+        //  p left   (id-1)        slot 3 (right)
+        //  p below  (id+ec)       slot 0 (up)
+        //  p right  (id+1)        slot 1 (left)
+        const int nb[4] = {id - g.ec, id - 1, id + g.ec, id + 1};
+        const unsigned slot[4] = {2u, 3u, 0u, 1u};
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        int p = nb[q];
-        if (st[p] == ST_SELECTED) {
-            unsigned long long k = ((unsigned long long)__float_as_uint(t[p]) << 32) | ((unsigned long long)cnt[p] << 2) | slot[q];
-            best = k < best ? k : best;
+        for (int q = 0; q < 4; q++) {
+            int p = nb[q];
+            if (st[p] == ST_SELECTED) {
+                unsigned long long k = ((unsigned long long)__float_as_uint(t[p]) << 32) | ((unsigned long long)cnt[p] << 2) | slot[q];
+                best = k < best ? k : best;
+            }
         }
     }
-    if (best == ~0ull) return;
-    unsigned pos = atomicAdd(n_new, 1u);
-    keys[pos] = best;
-    ids[pos] = (uint32_t)id;
+    // append (the sort that follows fixes the order): one global atomic per block
+    __shared__ unsigned wcount[8], base;
+    const bool hit = best != ~0ull;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wcount[w] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { unsigned c = wcount[k]; wcount[k] = tot; tot += c; }
+        base = tot ? atomicAdd(n_new, tot) : 0u;
+    }
+    __syncthreads();
+    if (hit) {
+        unsigned pos = base + wcount[w] + __popc(bal & ((1u << lane) - 1u));
+        keys[pos] = best;
+        ids[pos] = (uint32_t)id;
+    }
 }
 
 // after the sort: hand out push counters in fill order; the hole pass also records the fill order itself
@@ -224,7 +246,8 @@ __global__ void __launch_bounds__(256) ip_round(const uint32_t* __restrict__ ids
         tv[q] = k ? t[p] : T_FAR;  // an unreached pixel still carries T = 1e6 on the CPU at this moment
     }
     if (!ready) {
-        atomicAdd(pending, 1u);
+        const unsigned nb_ = __activemask();  // lanes that are not ready in this warp: one atomic for all of them
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(nb_) - 1)) atomicAdd(pending, (unsigned)__popc(nb_));
         return;
     }
     // min4(solve(i-1,j,i,j-1), solve(i+1,j,i,j-1), solve(i-1,j,i,j+1), solve(i+1,j,i,j+1))
@@ -954,8 +977,13 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
     ip_init<<<nblk, 256, 0, s>>>(mask, mask_stride, hole, t, cnt, rnd, done, &ctr->nholes, g);
     OFXCV_LAUNCH_CHECK(ctx);
     if (out != img) {
-        ip_copy<<<dim3(ofxcv_div_up(W * channels, 256), H), 256, 0, s>>>(img, img_stride, out, out_stride, W * channels, H);
-        OFXCV_LAUNCH_CHECK(ctx);
+        if (img_stride >= (ptrdiff_t)W * channels && out_stride >= (ptrdiff_t)W * channels) {  // the driver's pitched D2D copy
+            OFXCV_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)out_stride, img, (size_t)img_stride, (size_t)W * channels, H,
+                                              cudaMemcpyDeviceToDevice, s));
+        } else {  // bottom-up (negative stride) images
+            ip_copy<<<dim3(ofxcv_div_up(W * channels, 256), H), 256, 0, s>>>(img, img_stride, out, out_stride, W * channels, H);
+            OFXCV_LAUNCH_CHECK(ctx);
+        }
     }
     OFXCV_CUDA(ctx, cudaMemcpyAsync(hctr, ctr, sizeof(IpCounters), cudaMemcpyDeviceToHost, s));
     OFXCV_CUDA(ctx, cudaStreamSynchronize(s));

@@ -7,9 +7,10 @@
 //   -> dst[x*4+ch] = flow[x*2+c] / renderScale (VectorGenerator.cpp:494-519)
 // runs as sm_100a CUDA through the C ABI: frames are staged into HBM once per render (or used in place when the
 // host enables OFX CUDA render, ofxImageEffect.h:1013-1049).  Written against the raw OFX C API (no Support library).
+// The second method, Dual TV-L1 (VectorGenerator.cpp:436-492), runs through ofxcv_tvl1_u8 with the plugin's tau / lambda /
+// theta / nScales / warps / epsilon / iterations controls (parity of that method is unpinned: see the ABI header).
 // Deliberate differences, all documented in DESIGN.md: channels set to "0" are written as 0.0 (the reference leaves
-// them uninitialised); the whole row is converted (the pinned reference converts a quarter: SURVEY.md B1); the
-// Dual TV-L1 method is out of scope and returns kOfxStatErrUnsupported.
+// them uninitialised); the whole row is converted (the pinned reference converts a quarter: SURVEY.md B1).
 #include <math.h>
 #include <stdlib.h>
 
@@ -84,12 +85,12 @@ OfxStatus describe_in_context(OfxImageEffectHandle effect)
                         "Standard deviation of the Gaussian used to smooth derivatives used as a basis of the polynomial expansion. "
                         "For a Neighborhood of 5 you can set Sigma to 1.1, for 7 a good value would be 1.5.",
                         1.1, 0.1, 5);
-    // Dual TV-L1 controls: defined for project compatibility (VectorGenerator.cpp:874-929), hidden, unused
+    // Dual TV-L1 controls (VectorGenerator.cpp:874-929), hidden while the method is Farneback (updateVisibility, :642-662)
     const double tvd[6] = {0.25, 0.15, 0.3, 5, 5, 0.01};
     const char* tvl[6] = {"Tau", "Lambda", "Theta", "N. Scales", "Warps", "Epsilon"};
     for (int i = 0; i < 6; i++) {
-        if (i == 3 || i == 4) define_int(gHost, ps, kTvl1Names[i], tvl[i], "Dual TV-L1 parameter (method not available in this build)", (int)tvd[i], 1, 20);
-        else define_plain_double(gHost, ps, kTvl1Names[i], tvl[i], "Dual TV-L1 parameter (method not available in this build)", tvd[i], 0, 1);
+        if (i == 3 || i == 4) define_int(gHost, ps, kTvl1Names[i], tvl[i], "Dual TV-L1 parameter", (int)tvd[i], 1, 20);
+        else define_plain_double(gHost, ps, kTvl1Names[i], tvl[i], "Dual TV-L1 parameter", tvd[i], 0, 1);
         OfxParamHandle ph = nullptr;
         OfxPropertySetHandle pp = nullptr;
         if (gHost.param->paramGetHandle(ps, kTvl1Names[i], &ph, &pp) == kOfxStatOK && pp) P->propSetInt(pp, kOfxParamPropSecret, 0, 1);
@@ -184,7 +185,19 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
     int ch[4];
     bool fwd, bwd;
     read_channels(d, a.time, ch, fwd, bwd);
-    if (param_int(gHost, d->method, a.time) != 0) return kOfxStatErrUnsupported;
+    const int method = param_int(gHost, d->method, a.time);
+    if (method != 0 && method != 1) return kOfxStatErrUnsupported;
+    ofxcv_tvl1_params tv;
+    ofxcv_tvl1_default_params(&tv);
+    if (method == 1) {  // VectorGenerator.cpp:459-486
+        tv.tau = param_double(gHost, d->tvl1[0], a.time);
+        tv.lambda = param_double(gHost, d->tvl1[1], a.time);
+        tv.theta = param_double(gHost, d->tvl1[2], a.time);
+        tv.nscales = param_int(gHost, d->tvl1[3], a.time);
+        tv.warps = param_int(gHost, d->tvl1[4], a.time);
+        tv.epsilon = param_double(gHost, d->tvl1[5], a.time);
+        tv.iterations = param_int(gHost, d->iterations, a.time);
+    }
     ofxcv_fb_params par;
     ofxcv_fb_default_params(&par);
     par.levels = param_int(gHost, d->levels, a.time);
@@ -220,10 +233,15 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
         if (gHost.effect->abort(effect)) return kOfxStatOK;
         ImageGuard other(gHost, d->src, dir == 0 ? a.time + 1 : a.time - 1);
         stage_gray(ctx, other.img, win, dev, stage, d_float, (uint8_t*)d_gray1.p);
-        uint64_t key1 = 0;
-        check_cv(ofxcv_content_key_u8(ctx, nullptr, (const uint8_t*)d_gray1.p, W, W, H, &key1));
-        check_cv(ofxcv_farneback_u8_keyed(ctx, nullptr, (const uint8_t*)d_gray0.p, (const uint8_t*)d_gray1.p, W, W, H, (float*)d_flow.p,
-                                          (ptrdiff_t)W * 8, &par, key0, key1));
+        if (method == 1) {
+            check_cv(ofxcv_tvl1_u8(ctx, nullptr, (const uint8_t*)d_gray0.p, (const uint8_t*)d_gray1.p, W, W, H, (float*)d_flow.p,
+                                   (ptrdiff_t)W * 8, &tv));
+        } else {
+            uint64_t key1 = 0;
+            check_cv(ofxcv_content_key_u8(ctx, nullptr, (const uint8_t*)d_gray1.p, W, W, H, &key1));
+            check_cv(ofxcv_farneback_u8_keyed(ctx, nullptr, (const uint8_t*)d_gray0.p, (const uint8_t*)d_gray1.p, W, W, H,
+                                              (float*)d_flow.p, (ptrdiff_t)W * 8, &par, key0, key1));
+        }
         int sel[4];
         const int u = dir == 0 ? 1 : 3, v = dir == 0 ? 2 : 4;
         for (int c = 0; c < 4; c++) sel[c] = ch[c] == u ? 0 : ch[c] == v ? 1 : -1;
@@ -257,16 +275,18 @@ OfxStatus frames_needed(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs
 
 OfxStatus instance_changed(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
 {
-    // VectorGenerator.cpp:642-673: show the Farneback controls only for the Farneback method
+    // VectorGenerator.cpp:642-673: Farneback controls for Farneback, `iterations` for both methods, TV-L1 controls for TV-L1
     char* name = nullptr;
     if (gHost.prop->propGetString(inArgs, kOfxPropName, 0, &name) != kOfxStatOK || !name || strcmp(name, "method")) return kOfxStatReplyDefault;
     Instance* d = instance_data(effect);
     const int method = param_int(gHost, d->method, 0);
-    OfxParamHandle fb[4] = {d->levels, d->iterations, d->neighborhood, d->sigma};
-    for (OfxParamHandle h : fb) {
+    auto secret = [&](OfxParamHandle h, bool hide) {
         OfxPropertySetHandle pp = nullptr;
-        if (gHost.param->paramGetPropertySet(h, &pp) == kOfxStatOK && pp) gHost.prop->propSetInt(pp, kOfxParamPropSecret, 0, method != 0);
-    }
+        if (gHost.param->paramGetPropertySet(h, &pp) == kOfxStatOK && pp) gHost.prop->propSetInt(pp, kOfxParamPropSecret, 0, hide ? 1 : 0);
+    };
+    for (OfxParamHandle h : {d->levels, d->neighborhood, d->sigma}) secret(h, method != 0);
+    secret(d->iterations, method != 0 && method != 1);
+    for (OfxParamHandle h : d->tvl1) secret(h, method != 1);
     return kOfxStatOK;
 }
 

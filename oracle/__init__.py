@@ -9,6 +9,7 @@ Reference call sites restated (see each .c header):
   inpaint    /root/reference/opencv2fx/inpaint/inpaint.cpp:311-318   (+ NS per BASELINE.json)
   watershed  BASELINE.json config 3 (replaces /root/reference/opencv2fx/segment/segment.cpp:296-302)
   lut        /root/reference/SupportExt/ofxsLut.h:171-190,:220-223,:447-486
+  tvl1       /root/reference/VectorGenerator/VectorGenerator.cpp:436-492   (parity unpinned: see tvl1.c)
 """
 import ctypes as C
 import os
@@ -24,7 +25,7 @@ INPAINT_NS, INPAINT_TELEA = 0, 1
 
 def build(force=False):
     so = os.path.join(_HERE, "libofxcv_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("farneback.c", "watershed.c", "inpaint.c", "lut.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("farneback.c", "watershed.c", "inpaint.c", "lut.c", "tvl1.c")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libofxcv_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -106,6 +107,54 @@ def update_flow_blur(R0, R1, flow, M, winsize=3, update=True):
     lib().orc_update_flow_blur(_p(np.ascontiguousarray(R0, np.float32)), _p(np.ascontiguousarray(R1, np.float32)), _p(flow), _p(M),
                                C.c_int(w), C.c_int(h), C.c_int(winsize), C.c_int(1 if update else 0))
     return flow, M
+
+
+class Tvl1Params(C.Structure):
+    """Defaults = the plugin's (VectorGenerator.cpp:874-929; iterations :814) + OpenCV's fixed ones."""
+    _fields_ = [("tau", C.c_double), ("lambda_", C.c_double), ("theta", C.c_double), ("epsilon", C.c_double),
+                ("scale_step", C.c_double), ("nscales", C.c_int), ("warps", C.c_int), ("inner", C.c_int),
+                ("outer", C.c_int), ("median", C.c_int)]
+
+    def __init__(self, tau=0.25, lambda_=0.15, theta=0.3, epsilon=0.01, scale_step=0.8, nscales=5, warps=5, inner=15,
+                 outer=10, median=5):
+        super().__init__(tau, lambda_, theta, epsilon, scale_step, nscales, warps, inner, outer, median)
+
+
+def tvl1(prev, nxt, **kw):
+    """Dual TV-L1 flow prev -> nxt (HxW u8).  Returns (flow HxWx2 f32, inner iterations run)."""
+    prev = np.ascontiguousarray(prev, np.uint8); nxt = np.ascontiguousarray(nxt, np.uint8)
+    h, w = prev.shape
+    flow = np.empty((h, w, 2), np.float32)
+    par = Tvl1Params(**kw)
+    it = lib().orc_tvl1(_p(prev), _p(nxt), C.c_int(w), C.c_int(w), C.c_int(h), _p(flow), C.byref(par))
+    return flow, it
+
+
+def tvl1_resize(img, dw, dh, scale_x, scale_y):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    out = np.empty((dh, dw), np.float32)
+    lib().orc_tvl1_resize_f32(_p(img), C.c_int(w), C.c_int(h), _p(out), C.c_int(dw), C.c_int(dh), C.c_double(scale_x), C.c_double(scale_y))
+    return out
+
+
+def remap_cubic(img, mapx, mapy):
+    img = np.ascontiguousarray(img, np.float32)
+    mapx = np.ascontiguousarray(mapx, np.float32); mapy = np.ascontiguousarray(mapy, np.float32)
+    h, w = img.shape
+    dh, dw = mapx.shape
+    out = np.empty((dh, dw), np.float32)
+    src = (C.c_void_p * 1)(img.ctypes.data); dst = (C.c_void_p * 1)(out.ctypes.data)
+    lib().orc_remap_cubic_f32(src, C.c_int(1), C.c_int(w), C.c_int(h), _p(mapx), _p(mapy), dst, C.c_int(dw), C.c_int(dh))
+    return out
+
+
+def median5(img):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    out = np.empty_like(img)
+    lib().orc_median5_f32(_p(img), _p(out), C.c_int(w), C.c_int(h))
+    return out
 
 
 def watershed(img, markers):

@@ -67,6 +67,26 @@ def watershed():
     np.savez_compressed(os.path.join(HERE, "watershed_cv2.npz"), **out)
 
 
+def tvl1_primitives():
+    """The three cv2 primitives OpenCV's Dual TV-L1 is assembled from, on float images (the method itself is not in
+    cv2 4.13's main modules, so only its building blocks can be pinned)."""
+    rng = np.random.default_rng(11)
+    h, w = 61, 97
+    img = cv2.GaussianBlur((rng.random((h, w), dtype=np.float32) * 255).astype(np.float32), (0, 0), 1.5)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    mx = (xx + rng.standard_normal((h, w)).astype(np.float32) * 3).astype(np.float32)
+    my = (yy + rng.standard_normal((h, w)).astype(np.float32) * 3).astype(np.float32)
+    mx[0, :5] = -10; my[1, :5] = 200; mx[2, 0] = -1.2; mx[3, 0] = 96.7; mx[4, 0] = -2.99; mx[5, 0] = -3.0; mx[6, 0] = 97.0; mx[7, 0] = 98.0
+    out = {"img": img, "mapx": mx, "mapy": my,
+           "remap_cubic": cv2.remap(img, mx, my, cv2.INTER_CUBIC),
+           "median5": cv2.medianBlur(img, 5)}
+    noise = (rng.random((h, w), dtype=np.float32) * 255).astype(np.float32)
+    down = cv2.resize(noise, None, fx=0.8, fy=0.8, interpolation=cv2.INTER_LINEAR)
+    out["noise"], out["down08"] = noise, down
+    out["up"] = cv2.resize(down, (w, h), interpolation=cv2.INTER_LINEAR)
+    np.savez_compressed(os.path.join(HERE, "tvl1_primitives_cv2.npz"), **out)
+
+
 def lut():
     so = os.path.join(ROOT, "oracle", "_ref", "libofxs_lut_ref.so")
     L = C.CDLL(so)
@@ -95,7 +115,7 @@ def lut():
 
 if __name__ == "__main__":
     print("cv2", cv2.__version__)
-    farneback(); inpaint(); watershed(); lut()
+    farneback(); inpaint(); watershed(); lut(); tvl1_primitives()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

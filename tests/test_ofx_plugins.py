@@ -95,8 +95,11 @@ def test_vectorgenerator_descriptor(mh):
     p.set_param("method", 1)
     assert p.instance_changed("method") == 0
     assert p.param_prop("levels", "OfxParamPropSecret", instance=True)["int"] == 1
+    assert p.param_prop("iterations", "OfxParamPropSecret", instance=True)["int"] == 0   # shared by both methods
+    assert p.param_prop("tau", "OfxParamPropSecret", instance=True)["int"] == 0
     p.set_param("method", 0); p.instance_changed("method")
     assert p.param_prop("levels", "OfxParamPropSecret", instance=True)["int"] == 0
+    assert p.param_prop("warps", "OfxParamPropSecret", instance=True)["int"] == 1
     assert p.destroy_instance() == 0
     p.close()
 
@@ -252,11 +255,19 @@ def test_vectorgenerator_plugin_render(mh, oracle, synth):
     f2 = oracle.farneback(g[5], g[6], levels=2, iters=4)
     assert np.abs(dst2[..., 0] - f2[..., 1]).mean() <= 1e-3 and np.abs(dst2[..., 2] - f2[..., 0]).mean() <= 1e-3
     assert not dst2[..., 1].any() and not dst2[..., 3].any()
-    # frame t+1 missing -> kOfxStatFailed (VectorGenerator.cpp:563-566); TV-L1 -> unsupported
+    # frame t+1 missing -> kOfxStatFailed (VectorGenerator.cpp:563-566)
     p.clear_images("Source"); p.set_image("Source", 5, frames[5])
     assert p.render(5, (0, 0, w, h)) == mh.STAT_FAILED and p.images_outstanding() == 0
+    # Dual TV-L1 (VectorGenerator.cpp:436-492) with the plugin's controls: forward flow into R,G
     p.set_image("Source", 6, frames[6]); p.set_param("method", 1)
-    assert p.render(5, (0, 0, w, h)) == mh.STAT_ERR_UNSUPPORTED
+    p.set_param("rChannel", 1); p.set_param("gChannel", 2); p.set_param("bChannel", 0); p.set_param("aChannel", 0)
+    p.set_param("iterations", 6); p.set_param("warps", 2); p.set_param("nScales", 3); p.set_param("epsilon", 0.02)
+    dst3 = np.full((h, w, 4), 7.0, np.float32)
+    p.clear_images("Output"); p.set_image("Output", 5, dst3)
+    assert p.render(5, (0, 0, w, h)) == 0 and p.images_outstanding() == 0
+    tv, _ = oracle.tvl1(g[5], g[6], inner=6, warps=2, nscales=3, epsilon=0.02)
+    assert np.array_equal(dst3[..., 0], tv[..., 0]) and np.array_equal(dst3[..., 1], tv[..., 1])
+    assert not dst3[..., 2].any() and not dst3[..., 3].any()
     p.close()
 
 

@@ -102,3 +102,33 @@ def test_packed_conversions_match_reference_tables(oracle):
     assert np.array_equal(oracle.from_byte_packed(b.reshape(1, 256, 1))[0, :, 0], z["alpha_from"])
     # every 8-bit colour code survives the round trip (the reference patches its table for exactly this)
     assert np.array_equal(oracle.to_byte_packed(back, 4)[0, :, :3], np.stack([b, b, b], axis=-1))
+
+
+def test_tvl1_primitives_against_cv2(oracle):
+    """Dual TV-L1 itself cannot be pinned (no OpenCV build with it here: parity unpinned, see oracle/tvl1.c); the three
+    OpenCV primitives it is assembled from can: bicubic remap and the 5x5 median bit-exactly, the bilinear resize to
+    2 ulp (cv2's SIMD path contracts the two products differently)."""
+    z = np.load(os.path.join(G, "tvl1_primitives_cv2.npz"))
+    assert np.array_equal(oracle.remap_cubic(z["img"], z["mapx"], z["mapy"]), z["remap_cubic"])
+    assert np.array_equal(oracle.median5(z["img"]), z["median5"])
+    h, w = z["noise"].shape
+    dh, dw = z["down08"].shape
+    assert (dh, dw) == (round(h * 0.8), round(w * 0.8))
+    down = oracle.tvl1_resize(z["noise"], dw, dh, 1 / 0.8, 1 / 0.8)
+    assert np.abs(down - z["down08"]).max() <= 3.1e-5      # 2 ulp at 255
+    up = oracle.tvl1_resize(z["down08"], w, h, 1 / (w / dw), 1 / (h / dh))
+    assert np.abs(up - z["up"]).max() <= 3.1e-5
+
+
+def test_tvl1_oracle_recovers_a_translation(oracle, synth):
+    """Sanity of the restated method as a whole: a (2.5, -1.5) px shift of a smooth texture comes back to ~0.01 px, the
+    early exit is taken (fewer inner iterations than the 5 x 5 x 10 x 15 maximum), deterministic."""
+    base = synth.gray(synth.texture(120, 160, seed=3))
+    nxt = synth.shift_bilinear(base, 2.5, -1.5)
+    flow, iters = oracle.tvl1(base, nxt)
+    inner = flow[12:-12, 12:-12]
+    assert abs(np.median(inner[..., 0]) - 2.5) < 0.02 and abs(np.median(inner[..., 1]) + 1.5) < 0.02
+    assert np.abs(inner - np.array([2.5, -1.5], np.float32)).mean() < 0.05
+    assert 0 < iters < 5 * 5 * 10 * 15
+    flow2, iters2 = oracle.tvl1(base, nxt)
+    assert iters2 == iters and np.array_equal(flow, flow2)
