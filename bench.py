@@ -394,6 +394,34 @@ def bench_plugins(pkg, synth, ctx, W, H, with_cpu):
     finally:
         for c in ctxs:
             c.close()
+    # Dual TV-L1, the VectorGenerator plugin's second method (default parameters; parity of the method is unpinned)
+    base = synth.gray(synth.texture(H, W, seed=2000))
+    nxt = synth.shift_bilinear(base, 2.5, -1.5)
+    d_a, d_b, d_f = ctx.to_device(base), ctx.to_device(nxt), ctx.alloc(W * H * 8)
+    L = pkg.lib()
+    dt = gpu_time(lambda: ctx.tvl1_dev(d_a.ptr, d_b.ptr, W, H, d_f.ptr), 3)
+    ent = {"value": 1 / dt, "unit": "pairs/s", "ms_per_pair": dt * 1e3, "inner_iterations_run": int(L.ofxcv_tvl1_iterations_run(ctx.h)),
+           "workload": "%dx%d gray8 pair, plugin defaults (5 scales, 5 warps, 10 x 15 iterations, epsilon 0.01)" % (W, H)}
+    # the iteration kernel alone: every full-resolution launch of a run that cannot stop early
+    ctx.timing(True)
+    ctx.tvl1_dev(d_a.ptr, d_b.ptr, W, H, d_f.ptr, pkg.Tvl1Params(epsilon=0.0, warps=1, outer_iterations=2, nscales=1))
+    ctx.synchronize()
+    n_it, ms_it = ctx.kernel_time_ms(1)
+    ctx.timing(False)
+    if n_it:
+        us = ms_it * 1e3 / n_it
+        ent["iter_kernel"] = {"name": "tv_iter", "us_per_launch": us, "launches_timed": n_it,
+                              "algorithmic_gbs": L.ofxcv_tvl1_iter_bytes(W, H) / us / 1e3, "bytes_per_px": 64}
+    if with_cpu:
+        import oracle  # CPU port of the same method, timed on a 1/36-area sample (it is a scalar C loop)
+        sw, sh = W // 6, H // 6
+        sb = synth.gray(synth.texture(sh, sw, seed=2000))
+        sn = synth.shift_bilinear(sb, 2.5, -1.5)
+        t = time.perf_counter()
+        oracle.tvl1(sb, sn)
+        ent["cpu_port"] = {"pairs_per_s": 1 / (time.perf_counter() - t), "sample": "%dx%d (1/36 of the area), 1 core" % (sw, sh)}
+    out["tvl1"] = ent
+    d_a.free(); d_b.free(); d_f.free()
     mk = synth.seed_markers(H, W, 256, 5)
     for nf in (1, 512):
         d_rgbs, d_mks = ctx.alloc(W * H * 3 * nf), ctx.alloc(W * H * 4 * nf)

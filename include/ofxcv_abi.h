@@ -169,8 +169,8 @@ typedef struct ofxcv_tvl1_params {
 OFXCV_API void ofxcv_tvl1_default_params(ofxcv_tvl1_params* p);
 OFXCV_API int ofxcv_tvl1_scales(int W, int H, const ofxcv_tvl1_params* p);
 OFXCV_API size_t ofxcv_tvl1_workspace_bytes(int W, int H, const ofxcv_tvl1_params* p);
-/* algorithmic bytes of ONE full-resolution inner iteration (two launches): 88 B per pixel
- * (A 16 + U 8 in/8 out + P 16 read by the primal step; U 8 + P 16 in/16 out by the dual step). */
+/* algorithmic bytes of ONE full-resolution inner iteration (one launch): 64 B per pixel
+ * (in: warped-gradient plane 16 + flow 8 + dual variable 16; out: flow 8 + dual variable 16). */
 OFXCV_API double ofxcv_tvl1_iter_bytes(int W, int H);
 /* prev/next: 8-bit gray, `stride` bytes per row; flow: interleaved (dx,dy) float32, `flow_stride` BYTES/row, rows
  * 8-byte aligned.  Asynchronous on `stream` like ofxcv_farneback_u8; the convergence test stays on the device. */

@@ -41,7 +41,7 @@ struct ofxcv_ctx {
     // named device workspaces, grown on demand, reused between calls
     ofxcv_buf ws[56];
     // pinned host staging for the *_host entry points
-    ofxcv_buf pin[12];  // 0-3 internal staging, 4-11 ofxcv_scratch_pinned
+    ofxcv_buf pin[13];  // 0-3 internal staging, 4-11 ofxcv_scratch_pinned, 12 Dual TV-L1 stop flags
     // per-family kernel timing (bench.py roofline numerator): events recorded on the launching stream
     bool timing = false;
     std::vector<ofxcv_timed_launch> timed[3];
@@ -65,6 +65,7 @@ struct ofxcv_ctx {
     cudaEvent_t lane_done[2] = {nullptr, nullptr}, lane_start = nullptr;
     cudaEvent_t seq_ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int ip_fill_blocks_per_sm = 8;  // persistent CTAs of the inpaint fill kernel per SM (ofxcv_inpaint_set_fill_blocks)
+    cudaEvent_t tv_ev[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t tv_ctrl_off = 0;  // where the last ofxcv_tvl1_u8 put its control block inside WS_TV_ARENA
     int64_t inpaint_stats[4] = {0, 0, 0, 0};
     int64_t watershed_stats[4] = {0, 0, 0, 0};

@@ -143,6 +143,8 @@ void ofxcv_destroy(ofxcv_ctx* ctx)
     if (ctx->lane_start) cudaEventDestroy(ctx->lane_start);
     if (ctx->stream_up) cudaStreamDestroy(ctx->stream_up);
     if (ctx->stream_down) cudaStreamDestroy(ctx->stream_down);
+    for (auto& e : ctx->tv_ev)
+        if (e) cudaEventDestroy(e);
     for (auto& e : ctx->seq_ev)
         if (e) cudaEventDestroy(e);
     for (int f = 0; f < 3; f++)

@@ -10,14 +10,20 @@
 // HBM layout (per scale, row-major, no padding): I0, I1 float planes of the pyramid; J = float4 (I1, dI1/dx, dI1/dy, 0)
 // so that one bicubic tap of all three warped images is one LDG.128; A = float4 (I1wx, I1wy, |grad|^2, rho_c) written
 // once per warping and read once per inner iteration; U = float2 flow; P = float4 dual variable (p11, p12, p21, p22).
-// One inner iteration = two element-wise stencil kernels (88 B/px): tv_iter_u (threshold step + divergence + primal
-// update + squared-update partial sums) and tv_iter_p (forward gradient + dual update).  The convergence test
-// (error <= epsilon^2 * area stops the warping) never comes back to the host: the last block of tv_iter_u adds the
-// block partials in index order (f64, deterministic) and publishes the iteration at which to stop; later launches of
-// the same warping read it and return at once.
+// One inner iteration = ONE launch of tv_iter (64 B/px: A 16 + U 8 + P 16 in, U 8 + P 16 out): a warp walks a 31-column
+// strip (+1 halo lane) down a band of rows; the primal step of row y (threshold step + divergence of p + update of u +
+// squared-update sum) and the dual step of row y-1 (forward gradient of the NEW u + update of p) share the trip, the
+// vertical neighbours stay in registers, the horizontal ones come through warp shuffles, the next row is prefetched
+// while the current one is computed.  U and P are ping-pong pairs (a band reads only old values, so bands and strips
+// are independent); which half is current is a flag on the device, flipped by the last block of every launch that
+// actually ran.  The convergence test (error <= epsilon^2 * area stops the warping) never comes back to the host: the
+// last block adds the block partials in index order (f64, deterministic) and publishes the iteration at which to
+// stop; later launches of the same warping read it and return at once.
 #include <float.h>
 #include <limits.h>
 #include <math.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -25,7 +31,8 @@ namespace {
 
 struct TvCtrl {
     int stop_at;        // inner-iteration index (within the current warping) after which nothing runs; INT_MAX = none
-    unsigned ticket;    // blocks of tv_iter_u that have delivered their partial sum
+    unsigned ticket;    // blocks of the running launch that have finished (the last one publishes / flips)
+    int ucur, pcur;     // which half of the U / P ping-pong pair is current
     unsigned long long iters;  // inner iterations actually run (statistics)
     double err;         // squared update of the last iteration
 };
@@ -88,10 +95,11 @@ __global__ void __launch_bounds__(256) tv_grad_pack(const float* __restrict__ I,
 
 // one warping: bicubic remap of (I1, I1x, I1y) at (x + u1, y + u2) on the 1/32-pixel grid, constant border 0, then
 // grad = I1wx^2 + I1wy^2 and rho_c = I1w - I1wx u1 - I1wy u2 - I0.  Also re-arms the convergence control block.
-__global__ void __launch_bounds__(256) tv_warp(const float4* __restrict__ J, const float2* __restrict__ U, const float* __restrict__ I0,
-                                               float4* __restrict__ A, int w, int h, TvCtrl* __restrict__ ctrl)
+__global__ void __launch_bounds__(256) tv_warp(const float4* __restrict__ J, const float2* __restrict__ U0, const float2* __restrict__ U1,
+                                               const float* __restrict__ I0, float4* __restrict__ A, int w, int h, TvCtrl* __restrict__ ctrl)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const float2* __restrict__ U = ctrl->ucur ? U1 : U0;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         ctrl->stop_at = INT_MAX;
         ctrl->ticket = 0;
@@ -139,78 +147,174 @@ __global__ void __launch_bounds__(256) tv_warp(const float4* __restrict__ J, con
     A[o] = make_float4(s1, s2, s1 * s1 + s2 * s2, s0 - s1 * u.x - s2 * u.y - I0[o]);
 }
 
-// 5x5 median of both flow components (replicated border).  rank selection: the median is the value with exactly 12
-// predecessors in the order (value, window index).  Passes the flow through unchanged once the warping has stopped,
-// so that the host can swap the two buffers unconditionally.
-__global__ void __launch_bounds__(256) tv_median5(const float2* __restrict__ U, float2* __restrict__ out, int w, int h, int iter,
-                                                  const TvCtrl* __restrict__ ctrl)
+// 5x5 median of both flow components (replicated border) by forgetful selection: keep 14 candidates, drop their
+// minimum and maximum, add the next value, ... until one is left (168 compare-exchanges per component; the median of a
+// multiset does not depend on how it is found).  Passes the flow through unchanged once the warping has stopped, so
+// that the host can swap the two buffers unconditionally.
+__device__ __forceinline__ void tv_cswap(float& a, float& b)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    const size_t o = (size_t)y * w + x;
-    if (iter > ctrl->stop_at) {
-        out[o] = U[o];
-        return;
-    }
-    float a[25], b[25];
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = lo;
+    b = hi;
+}
+template <int N>
+__device__ __forceinline__ void tv_minmax_to_ends(float (&v)[14])  // minimum to v[0], maximum to v[N-1]
+{
 #pragma unroll
-    for (int dy = -2; dy <= 2; dy++)
+    for (int i = 0; i < N - 1; i++) tv_cswap(v[i], v[i + 1]);
 #pragma unroll
-        for (int dx = -2; dx <= 2; dx++) {
-            const int yy = min(max(y + dy, 0), h - 1), xx = min(max(x + dx, 0), w - 1);
-            const float2 v = U[(size_t)yy * w + xx];
-            a[(dy + 2) * 5 + dx + 2] = v.x;
-            b[(dy + 2) * 5 + dx + 2] = v.y;
-        }
-    float ma = a[12], mb = b[12];
+    for (int i = N - 2; i > 0; i--) tv_cswap(v[i - 1], v[i]);
+}
+__device__ __forceinline__ float tv_median25(const float (&a)[25])
+{
+    float v[14];
 #pragma unroll
-    for (int i = 0; i < 25; i++) {
-        int ra = 0, rb = 0;
-#pragma unroll
-        for (int j = 0; j < 25; j++) {
-            ra += (a[j] < a[i]) || (a[j] == a[i] && j < i);
-            rb += (b[j] < b[i]) || (b[j] == b[i] && j < i);
-        }
-        if (ra == 12) ma = a[i];
-        if (rb == 12) mb = b[i];
-    }
-    out[o] = make_float2(ma, mb);
+    for (int i = 0; i < 14; i++) v[i] = a[i];
+    // after each step the survivors sit in v[1..N-2]; the next value replaces the dropped minimum
+    tv_minmax_to_ends<14>(v); v[0] = a[14];
+    tv_minmax_to_ends<13>(v); v[0] = a[15];
+    tv_minmax_to_ends<12>(v); v[0] = a[16];
+    tv_minmax_to_ends<11>(v); v[0] = a[17];
+    tv_minmax_to_ends<10>(v); v[0] = a[18];
+    tv_minmax_to_ends<9>(v); v[0] = a[19];
+    tv_minmax_to_ends<8>(v); v[0] = a[20];
+    tv_minmax_to_ends<7>(v); v[0] = a[21];
+    tv_minmax_to_ends<6>(v); v[0] = a[22];
+    tv_minmax_to_ends<5>(v); v[0] = a[23];
+    tv_minmax_to_ends<4>(v); v[0] = a[24];
+    tv_minmax_to_ends<3>(v);
+    return v[1];
 }
 
-// threshold step (estimateV) + divergence of p + primal update (estimateU), in place on U; squared update summed in f64
-__global__ void __launch_bounds__(256) tv_iter_u(const float4* __restrict__ A, const float4* __restrict__ P, float2* __restrict__ U, int w, int h,
-                                                 float l_t, float theta, float scaled_eps, int iter, TvCtrl* __restrict__ ctrl,
-                                                 double* __restrict__ partials)
+__global__ void __launch_bounds__(256) tv_median5(float2* __restrict__ U0, float2* __restrict__ U1, int w, int h, int iter, TvCtrl* __restrict__ ctrl)
 {
     if (iter > ctrl->stop_at) return;
+    const int cur = ctrl->ucur;
+    const float2* __restrict__ U = cur ? U1 : U0;
+    float2* __restrict__ out = cur ? U0 : U1;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    double e = 0.;
     if (x < w) {
-        const size_t i = (size_t)y * w + x;
-        const float4 a = A[i];  // I1wx, I1wy, grad, rho_c
-        const float2 u = U[i];
-        const float4 p = P[i];
-        const float rho = a.w + (a.x * u.x + a.y * u.y);
-        float d1 = 0.f, d2 = 0.f;
-        const float lg = l_t * a.z;
-        if (rho < -lg) { d1 = l_t * a.x; d2 = l_t * a.y; }
-        else if (rho > lg) { d1 = -l_t * a.x; d2 = -l_t * a.y; }
-        else if (a.z > FLT_EPSILON) { const float fi = -rho / a.z; d1 = fi * a.x; d2 = fi * a.y; }
-        const float v1 = u.x + d1, v2 = u.y + d2;
-        float a1 = p.x, b1 = p.y, a2 = p.z, b2 = p.w;
-        if (x > 0) { const float4 pl = P[i - 1]; a1 = p.x - pl.x; a2 = p.z - pl.z; }
-        if (y > 0) { const float4 pu = P[i - w]; b1 = p.y - pu.y; b2 = p.w - pu.w; }
-        const float n1 = v1 + theta * (a1 + b1), n2 = v2 + theta * (a2 + b2);
-        const float e1 = n1 - u.x, e2 = n2 - u.y;
-        e = (double)(e1 * e1 + e2 * e2);
-        U[i] = make_float2(n1, n2);
+        float a[25], b[25];
+#pragma unroll
+        for (int dy = -2; dy <= 2; dy++)
+#pragma unroll
+            for (int dx = -2; dx <= 2; dx++) {
+                const int yy = min(max(y + dy, 0), h - 1), xx = min(max(x + dx, 0), w - 1);
+                const float2 v = U[(size_t)yy * w + xx];
+                a[(dy + 2) * 5 + dx + 2] = v.x;
+                b[(dy + 2) * 5 + dx + 2] = v.y;
+            }
+        out[(size_t)y * w + x] = make_float2(tv_median25(a), tv_median25(b));
     }
-    // block sum -> partials[block]; the last block to arrive adds the partials in index order
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&ctrl->ticket, 1u) == gridDim.x * gridDim.y - 1) {  // every block has read `ucur` by now
+            ctrl->ticket = 0;
+            ctrl->ucur = cur ^ 1;
+        }
+    }
+}
+
+// one inner iteration (see the header of this file).  Geometry: warp = strip of 31 columns (lane 31 = right halo: it
+// computes the new u of the next strip's first column, which the dual step of column 30 needs), block = 8 adjacent
+// strips x one band of `rb` rows (+ the new u of the row below the band, not stored).
+constexpr int TV_STRIP = 31;
+struct TvRow {
+    float4 a, p;   // (I1wx, I1wy, grad, rho_c), (p11, p12, p21, p22) of this lane's pixel
+    float2 u, pl;  // flow; (p11, p21) of the pixel left of the strip (lane 0 only)
+};
+__device__ __forceinline__ void tv_load_row(TvRow& r, const float4* __restrict__ A, const float4* __restrict__ P, const float2* __restrict__ U,
+                                            int x, int y, int w, bool inx, int lane)
+{
+    r.a = r.p = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.u = r.pl = make_float2(0.f, 0.f);
+    if (inx) {
+        const size_t i = (size_t)y * w + x;
+        r.a = __ldcs(&A[i]);
+        r.p = P[i];
+        r.u = U[i];
+        if (lane == 0 && x > 0) {
+            const float4 t = P[i - 1];
+            r.pl = make_float2(t.x, t.z);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) tv_iter(const float4* __restrict__ A, float4* __restrict__ P0, float4* __restrict__ P1, float2* __restrict__ U0,
+                                               float2* __restrict__ U1, int w, int h, int rb, float l_t, float theta, float taut,
+                                               float scaled_eps, int iter, TvCtrl* __restrict__ ctrl, double* __restrict__ partials)
+{
+    if (iter > ctrl->stop_at) return;
+    const int ucur = ctrl->ucur, pcur = ctrl->pcur;
+    const float2* __restrict__ Ui = ucur ? U1 : U0;
+    float2* __restrict__ Uo = ucur ? U0 : U1;
+    const float4* __restrict__ Pi = pcur ? P1 : P0;
+    float4* __restrict__ Po = pcur ? P0 : P1;
+    const int lane = threadIdx.x & 31, strip = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int x = strip * TV_STRIP + lane, y0 = blockIdx.y * rb, y1 = min(y0 + rb, h);
+    const bool inx = x < w, owner = inx && lane < TV_STRIP;
+    double e = 0.;
+    if (strip * TV_STRIP < w) {
+        float pu_y = 0.f, pu_w = 0.f;  // p12, p22 of the row above
+        if (y0 > 0 && inx) {
+            const float4 t = Pi[(size_t)(y0 - 1) * w + x];
+            pu_y = t.y;
+            pu_w = t.w;
+        }
+        TvRow nxt;
+        tv_load_row(nxt, A, Pi, Ui, x, y0, w, inx, lane);
+        float4 p_prev = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 n_prev = make_float2(0.f, 0.f), nr_prev = make_float2(0.f, 0.f);
+        for (int y = y0; y <= y1; y++) {
+            const bool have = y < h;  // y == y1 is the row below the band (or below the image)
+            const TvRow c = nxt;
+            if (y + 1 <= y1 && y + 1 < h) tv_load_row(nxt, A, Pi, Ui, x, y + 1, w, inx, lane);
+            float2 n = make_float2(0.f, 0.f);
+            if (have) {
+                // ---- primal step of row y: estimateV + divergence + estimateU
+                float plx = __shfl_up_sync(0xffffffffu, c.p.x, 1), plz = __shfl_up_sync(0xffffffffu, c.p.z, 1);
+                if (lane == 0) { plx = c.pl.x; plz = c.pl.y; }
+                const float rho = c.a.w + (c.a.x * c.u.x + c.a.y * c.u.y);
+                float d1 = 0.f, d2 = 0.f;
+                const float lg = l_t * c.a.z;
+                if (rho < -lg) { d1 = l_t * c.a.x; d2 = l_t * c.a.y; }
+                else if (rho > lg) { d1 = -l_t * c.a.x; d2 = -l_t * c.a.y; }
+                else if (c.a.z > FLT_EPSILON) { const float fi = -rho / c.a.z; d1 = fi * c.a.x; d2 = fi * c.a.y; }
+                const float v1 = c.u.x + d1, v2 = c.u.y + d2;
+                const float a1 = x > 0 ? c.p.x - plx : c.p.x, a2 = x > 0 ? c.p.z - plz : c.p.z;
+                const float b1 = y > 0 ? c.p.y - pu_y : c.p.y, b2 = y > 0 ? c.p.w - pu_w : c.p.w;
+                n = make_float2(v1 + theta * (a1 + b1), v2 + theta * (a2 + b2));
+                if (owner && y < y1) {
+                    const float e1 = n.x - c.u.x, e2 = n.y - c.u.y;
+                    e += (double)(e1 * e1 + e2 * e2);
+                    Uo[(size_t)y * w + x] = n;
+                }
+            }
+            if (y > y0) {
+                // ---- dual step of row y-1: forward gradient of the new u + estimateDualVariables
+                float u1x = 0.f, u2x = 0.f, u1y = 0.f, u2y = 0.f;
+                if (x + 1 < w) { u1x = nr_prev.x - n_prev.x; u2x = nr_prev.y - n_prev.y; }
+                if (have) { u1y = n.x - n_prev.x; u2y = n.y - n_prev.y; }
+                const float g1 = (float)sqrt((double)u1x * (double)u1x + (double)u1y * (double)u1y);
+                const float g2 = (float)sqrt((double)u2x * (double)u2x + (double)u2y * (double)u2y);
+                const float ng1 = 1.f + taut * g1, ng2 = 1.f + taut * g2;
+                if (owner)
+                    Po[(size_t)(y - 1) * w + x] = make_float4((p_prev.x + taut * u1x) / ng1, (p_prev.y + taut * u1y) / ng1,
+                                                              (p_prev.z + taut * u2x) / ng2, (p_prev.w + taut * u2y) / ng2);
+            }
+            p_prev = c.p;
+            pu_y = c.p.y;
+            pu_w = c.p.w;
+            n_prev = n;
+            nr_prev = make_float2(__shfl_down_sync(0xffffffffu, n.x, 1), __shfl_down_sync(0xffffffffu, n.y, 1));
+        }
+    }
+    // block sum -> partials[block]; the last block to arrive adds the partials in index order, publishes, flips
     __shared__ double wsum[8];
     __shared__ bool last;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(0xffffffffu, e, d);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = e;
+    if (lane == 0) wsum[threadIdx.x >> 5] = e;
     __syncthreads();
     const unsigned nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
     if (threadIdx.x == 0) {
@@ -226,10 +330,9 @@ __global__ void __launch_bounds__(256) tv_iter_u(const float4* __restrict__ A, c
     __threadfence();
     double s = 0.;
     for (unsigned k = threadIdx.x; k < nblocks; k += blockDim.x) s += __ldcg(&partials[k]);
-    // fixed-shape tree over the 256 strided sums
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    if (lane == 0) wsum[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.;
@@ -238,37 +341,19 @@ __global__ void __launch_bounds__(256) tv_iter_u(const float4* __restrict__ A, c
         ctrl->err = t;
         ctrl->iters += 1;
         ctrl->ticket = 0;
-        if (!(t > (double)scaled_eps)) ctrl->stop_at = iter;  // this iteration's dual update still runs
+        ctrl->ucur = ucur ^ 1;  // every block has read the flags by now
+        ctrl->pcur = pcur ^ 1;
+        if (!(t > (double)scaled_eps)) ctrl->stop_at = iter;
     }
 }
 
-// forward gradient of u + dual update, in place on P
-__global__ void __launch_bounds__(256) tv_iter_p(const float2* __restrict__ U, float4* __restrict__ P, int w, int h, float taut, int iter,
-                                                 const TvCtrl* __restrict__ ctrl)
-{
-    if (iter > ctrl->stop_at) return;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    const size_t i = (size_t)y * w + x;
-    const float2 u = U[i];
-    float u1x = 0.f, u2x = 0.f, u1y = 0.f, u2y = 0.f;
-    if (x + 1 < w) { const float2 r = U[i + 1]; u1x = r.x - u.x; u2x = r.y - u.y; }
-    if (y + 1 < h) { const float2 d = U[i + w]; u1y = d.x - u.x; u2y = d.y - u.y; }
-    const float g1 = (float)sqrt((double)u1x * (double)u1x + (double)u1y * (double)u1y);
-    const float g2 = (float)sqrt((double)u2x * (double)u2x + (double)u2y * (double)u2y);
-    const float ng1 = 1.f + taut * g1, ng2 = 1.f + taut * g2;
-    float4 p = P[i];
-    p.x = (p.x + taut * u1x) / ng1;
-    p.y = (p.y + taut * u1y) / ng1;
-    p.z = (p.z + taut * u2x) / ng2;
-    p.w = (p.w + taut * u2y) / ng2;
-    P[i] = p;
-}
-
-__global__ void __launch_bounds__(256) tv_store_flow(const float2* __restrict__ U, char* __restrict__ flow, ptrdiff_t flow_stride, int w, int h)
+// out = current half of the U pair (the final flow, or the source of the resize to the next finer scale)
+__global__ void __launch_bounds__(256) tv_store_flow(const float2* __restrict__ U0, const float2* __restrict__ U1, const TvCtrl* __restrict__ ctrl,
+                                                     char* __restrict__ flow, ptrdiff_t flow_stride, int w, int h)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
+    const float2* __restrict__ U = ctrl->ucur ? U1 : U0;
     reinterpret_cast<float2*>(flow + (ptrdiff_t)y * flow_stride)[x] = U[(size_t)y * w + x];
 }
 
@@ -278,7 +363,7 @@ constexpr int TV_MAXS = 32;
 struct TvPlan {
     int ns, w[TV_MAXS], h[TV_MAXS];
     size_t off_i0[TV_MAXS], off_i1[TV_MAXS];  // float offsets into the arena
-    size_t off_j, off_a, off_u, off_u2, off_p, off_uc, off_part, off_ctrl, total;  // byte offsets
+    size_t off_j, off_a, off_u, off_u2, off_p, off_p2, off_uc, off_part, off_ctrl, total;  // byte offsets
 };
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -307,10 +392,11 @@ int tv_plan(int W, int H, const ofxcv_tvl1_params* p, TvPlan* pl)
     pl->off_j = off; off = align256(off + n0 * 16);
     pl->off_a = off; off = align256(off + n0 * 16);
     pl->off_p = off; off = align256(off + n0 * 16);
+    pl->off_p2 = off; off = align256(off + n0 * 16);
     pl->off_u = off; off = align256(off + n0 * 8);
     pl->off_u2 = off; off = align256(off + n0 * 8);
     pl->off_uc = off; off = align256(off + n0 * 8);  // flow of the coarser scale (resize source)
-    pl->off_part = off; off = align256(off + (size_t)ofxcv_div_up(W, 256) * H * 8);
+    pl->off_part = off; off = align256(off + (size_t)(ofxcv_div_up(W, 8 * TV_STRIP) + 1) * (H / 4 + 2) * 8);  // one per tv_iter block
     pl->off_ctrl = off; off = align256(off + sizeof(TvCtrl));
     pl->total = off;
     return built;
@@ -353,7 +439,7 @@ size_t ofxcv_tvl1_workspace_bytes(int W, int H, const ofxcv_tvl1_params* params)
     return pl.total;
 }
 
-double ofxcv_tvl1_iter_bytes(int W, int H) { return 88.0 * (double)W * (double)H; }
+double ofxcv_tvl1_iter_bytes(int W, int H) { return 64.0 * (double)W * (double)H; }
 
 int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, const uint8_t* next, ptrdiff_t stride, int W, int H,
                   float* flow, ptrdiff_t flow_stride, const ofxcv_tvl1_params* params)
@@ -390,9 +476,10 @@ int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, cons
     ctx->tv_ctrl_off = pl.off_ctrl;
     float4* J = (float4*)(base + pl.off_j);
     float4* A = (float4*)(base + pl.off_a);
-    float4* Pd = (float4*)(base + pl.off_p);
-    float2* U = (float2*)(base + pl.off_u);
-    float2* U2 = (float2*)(base + pl.off_u2);
+    float4* Pa = (float4*)(base + pl.off_p);
+    float4* Pb = (float4*)(base + pl.off_p2);
+    float2* Ua = (float2*)(base + pl.off_u);
+    float2* Ub = (float2*)(base + pl.off_u2);
     float2* Uc = (float2*)(base + pl.off_uc);
     double* partials = (double*)(base + pl.off_part);
     TvCtrl* ctrl = (TvCtrl*)(base + pl.off_ctrl);
@@ -400,6 +487,15 @@ int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, cons
     auto I1 = [&](int k) { return (float*)(base + pl.off_i1[k]); };
     auto grid = [](int w, int h) { return dim3(ofxcv_div_up(w, 256), h); };
 
+    // The convergence flag lives on the device; the host only PEEKS at it: after every outer iteration the flag is copied
+    // to pinned memory behind an event, and before enqueuing more work the host looks at the copies whose events have
+    // already completed.  A warping that has stopped then costs no further (no-op) launches when the host is the
+    // bottleneck, and nothing changes when the GPU is: the launches that are skipped would have returned at once.
+    constexpr int TV_NEV = 16;
+    int* h_stop = (int*)ofxcv_pin(ctx, 12, TV_NEV * sizeof(int));
+    if (!h_stop) return OFXCV_ERR_MEMORY;
+    for (auto& e : ctx->tv_ev)
+        if (!e) OFXCV_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ofxcv_prof_scope ps_all(ctx, s, "tv_total", 0);
     OFXCV_CUDA(ctx, cudaMemsetAsync(ctrl, 0, sizeof(TvCtrl), s));
     tv_u8_to_f32<<<grid(W, H), 256, 0, s>>>(prev, next, stride, I0(0), I1(0), W, H);
@@ -418,45 +514,64 @@ int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, cons
         const size_t n = (size_t)w * h;
         const dim3 g = grid(w, h);
         const float scaled_eps = (float)(P.epsilon * P.epsilon * (double)n);
+        // rows per band of tv_iter: short enough for ~48 warps per SM (a band costs one redundant halo row), 4..32
+        const long long strips = ofxcv_div_up(w, TV_STRIP);
+        const int rb = (int)std::min<long long>(32, std::max<long long>(4, (long long)h * strips / (48LL * ctx->num_sms)));
+        const dim3 gi(ofxcv_div_up(ofxcv_div_up(w, TV_STRIP), 8), ofxcv_div_up(h, rb));
         if (k == pl.ns - 1) {
-            OFXCV_CUDA(ctx, cudaMemsetAsync(U, 0, n * 8, s));
-        } else {  // flow of the coarser scale, resized and multiplied by 1 / scaleStep
+            OFXCV_CUDA(ctx, cudaMemsetAsync(Ua, 0, n * 8, s));
+        } else {  // flow of the coarser scale (current half -> Uc), resized and multiplied by 1 / scaleStep
             const int cw = pl.w[k + 1], ch = pl.h[k + 1];
-            OFXCV_CUDA(ctx, cudaMemcpyAsync(Uc, U, (size_t)cw * ch * 8, cudaMemcpyDeviceToDevice, s));
-            tv_resize<2><<<g, 256, 0, s>>>((const float*)Uc, cw, ch, (float*)U, w, h, 1. / ((double)w / cw), 1. / ((double)h / ch), up, 1);
+            tv_store_flow<<<grid(cw, ch), 256, 0, s>>>(Ua, Ub, ctrl, (char*)Uc, (ptrdiff_t)cw * 8, cw, ch);
+            OFXCV_LAUNCH_CHECK(ctx);
+            tv_resize<2><<<g, 256, 0, s>>>((const float*)Uc, cw, ch, (float*)Ua, w, h, 1. / ((double)w / cw), 1. / ((double)h / ch), up, 1);
             OFXCV_LAUNCH_CHECK(ctx);
         }
         tv_grad_pack<<<g, 256, 0, s>>>(I1(k), J, w, h);
         OFXCV_LAUNCH_CHECK(ctx);
-        OFXCV_CUDA(ctx, cudaMemsetAsync(Pd, 0, n * 16, s));
+        OFXCV_CUDA(ctx, cudaMemsetAsync(Pa, 0, n * 16, s));
+        OFXCV_CUDA(ctx, cudaMemsetAsync(&ctrl->ucur, 0, 2 * sizeof(int), s));  // current halves: Ua, Pa
         for (int wi = 0; wi < P.warps; wi++) {
             {
                 ofxcv_prof_scope ps(ctx, s, "tv_warp", k);
-                tv_warp<<<g, 256, 0, s>>>(J, U, I0(k), A, w, h, ctrl);
+                tv_warp<<<g, 256, 0, s>>>(J, Ua, Ub, I0(k), A, w, h, ctrl);
                 OFXCV_LAUNCH_CHECK(ctx);
             }
-            int it = 0;
+            int it = 0, ev_head = 0, ev_tail = 0;  // flag copies of THIS warping still in flight: [ev_head, ev_tail)
+            bool stopped = false;
+            auto peek = [&]() {
+                while (ev_head < ev_tail && cudaEventQuery(ctx->tv_ev[ev_head % TV_NEV]) == cudaSuccess) {
+                    if (h_stop[ev_head % TV_NEV] != INT_MAX) stopped = true;
+                    ev_head++;
+                }
+                cudaGetLastError();  // cudaErrorNotReady is not an error
+            };
             for (int no = 0; no < P.outer_iterations; no++) {
+                peek();
+                if (stopped) break;
                 if (P.median_filtering > 1) {
                     ofxcv_prof_scope ps(ctx, s, "tv_median5", k);
-                    tv_median5<<<g, 256, 0, s>>>(U, U2, w, h, it, ctrl);
+                    tv_median5<<<g, 256, 0, s>>>(Ua, Ub, w, h, it, ctrl);
                     OFXCV_LAUNCH_CHECK(ctx);
-                    float2* t = U; U = U2; U2 = t;
                 }
                 ofxcv_prof_scope ps(ctx, s, "tv_iter", k);
                 for (int ni = 0; ni < P.iterations; ni++, it++) {
                     const bool timed = ctx->timing && k == 0;
                     if (timed) ofxcv_time_begin(ctx, 1, s);
-                    tv_iter_u<<<g, 256, 0, s>>>(A, Pd, U, w, h, l_t, theta, scaled_eps, it, ctrl, partials);
-                    OFXCV_LAUNCH_CHECK(ctx);
-                    tv_iter_p<<<g, 256, 0, s>>>(U, Pd, w, h, taut, it, ctrl);
+                    tv_iter<<<gi, 256, 0, s>>>(A, Pa, Pb, Ua, Ub, w, h, rb, l_t, theta, taut, scaled_eps, it, ctrl, partials);
                     OFXCV_LAUNCH_CHECK(ctx);
                     if (timed) ofxcv_time_end(ctx, 1, s);
+                }
+                if (ev_tail - ev_head < TV_NEV && no + 1 < P.outer_iterations) {
+                    const int slot = ev_tail % TV_NEV;
+                    OFXCV_CUDA(ctx, cudaMemcpyAsync(&h_stop[slot], &ctrl->stop_at, sizeof(int), cudaMemcpyDeviceToHost, s));
+                    OFXCV_CUDA(ctx, cudaEventRecord(ctx->tv_ev[slot], s));
+                    ev_tail++;
                 }
             }
         }
     }
-    tv_store_flow<<<grid(W, H), 256, 0, s>>>(U, (char*)flow, flow_stride, W, H);
+    tv_store_flow<<<grid(W, H), 256, 0, s>>>(Ua, Ub, ctrl, (char*)flow, flow_stride, W, H);
     OFXCV_LAUNCH_CHECK(ctx);
     return OFXCV_OK;
 }
