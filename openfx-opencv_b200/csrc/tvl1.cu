@@ -22,6 +22,7 @@
 #include <float.h>
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -240,7 +241,8 @@ __device__ __forceinline__ void tv_load_row(TvRow& r, const float4* __restrict__
         }
     }
 }
-__global__ void __launch_bounds__(256) tv_iter(const float4* __restrict__ A, float4* __restrict__ P0, float4* __restrict__ P1, float2* __restrict__ U0,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) tv_iter(const float4* __restrict__ A, float4* __restrict__ P0, float4* __restrict__ P1, float2* __restrict__ U0,
                                                float2* __restrict__ U1, int w, int h, int rb, float l_t, float theta, float taut,
                                                float scaled_eps, int iter, TvCtrl* __restrict__ ctrl, double* __restrict__ partials)
 {
@@ -514,9 +516,13 @@ int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, cons
         const size_t n = (size_t)w * h;
         const dim3 g = grid(w, h);
         const float scaled_eps = (float)(P.epsilon * P.epsilon * (double)n);
-        // rows per band of tv_iter: short enough for ~48 warps per SM (a band costs one redundant halo row), 4..32
+        // rows per band of tv_iter: short enough for ~48 warps per SM (a band costs one redundant halo row), 4..16
+        // (measured at 4K: 121 us for 12-16 rows, 126-128 us for 8 or 24-32 rows)
         const long long strips = ofxcv_div_up(w, TV_STRIP);
-        const int rb = (int)std::min<long long>(32, std::max<long long>(4, (long long)h * strips / (48LL * ctx->num_sms)));
+        int rb = (int)std::min<long long>(16, std::max<long long>(4, (long long)h * strips / (48LL * ctx->num_sms)));
+        static const int env_rb = getenv("OFXCV_TV_RB") ? atoi(getenv("OFXCV_TV_RB")) : 0;       // experiments
+        static const int env_minb = getenv("OFXCV_TV_MINB") ? atoi(getenv("OFXCV_TV_MINB")) : 4;
+        if (env_rb > 0) rb = env_rb;
         const dim3 gi(ofxcv_div_up(ofxcv_div_up(w, TV_STRIP), 8), ofxcv_div_up(h, rb));
         if (k == pl.ns - 1) {
             OFXCV_CUDA(ctx, cudaMemsetAsync(Ua, 0, n * 8, s));
@@ -558,7 +564,10 @@ int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, cons
                 for (int ni = 0; ni < P.iterations; ni++, it++) {
                     const bool timed = ctx->timing && k == 0;
                     if (timed) ofxcv_time_begin(ctx, 1, s);
-                    tv_iter<<<gi, 256, 0, s>>>(A, Pa, Pb, Ua, Ub, w, h, rb, l_t, theta, taut, scaled_eps, it, ctrl, partials);
+                    if (env_minb == 5)
+                        tv_iter<5><<<gi, 256, 0, s>>>(A, Pa, Pb, Ua, Ub, w, h, rb, l_t, theta, taut, scaled_eps, it, ctrl, partials);
+                    else
+                        tv_iter<4><<<gi, 256, 0, s>>>(A, Pa, Pb, Ua, Ub, w, h, rb, l_t, theta, taut, scaled_eps, it, ctrl, partials);
                     OFXCV_LAUNCH_CHECK(ctx);
                     if (timed) ofxcv_time_end(ctx, 1, s);
                 }

@@ -1,5 +1,5 @@
 """Turn one kernel of an .ncu-rep into the small JSON + markdown summary committed under profiles/.
-usage: ncu_to_profile.py rep out_prefix width height [kernel_index]"""
+usage: ncu_to_profile.py rep out_prefix width height [kernel_index [bytes_per_px]]"""
 import csv, io, json, subprocess, sys
 rep, out, W, H = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
 ki = int(sys.argv[5]) if len(sys.argv) > 5 else 0
@@ -31,7 +31,7 @@ d = {
                          for i, h in enumerate(hdr) if "issue_stalled" in h and "per_issue_active" in h and "not_issued" not in h and float(vals[i] or 0) >= 0.05},
     "command": "ncu --set full --clock-control none --import-source on (see the .md beside this file)",
 }
-alg = 88.0 * W * H
+alg = (float(sys.argv[6]) if len(sys.argv) > 6 else 88.0) * W * H
 d["algorithmic_bytes_per_launch"] = alg
 d["algorithmic_gbs_this_launch"] = alg / d["gpu_time_us"] / 1e3
 json.dump(d, open(out + ".json", "w"), indent=1)
