@@ -8,6 +8,8 @@ ctx = p.Context(0)
 base = s.gray(s.texture(H, W, seed=2000)); nxt = s.shift_bilinear(base, 2.5, -1.5)
 d0, d1, df = ctx.to_device(base), ctx.to_device(nxt), ctx.alloc(W * H * 8)
 ctx.farneback_dev(d0.ptr, d1.ptr, W, H, df.ptr); ctx.synchronize()
+ctx.tvl1_dev(d0.ptr, d1.ptr, W, H, df.ptr, p.Tvl1Params(epsilon=0.0, nscales=2, warps=1, outer_iterations=1, iterations=3)); ctx.synchronize()
+ctx.farneback_dev(d0.ptr, d1.ptr, W, H, df.ptr); ctx.synchronize()
 img = s.texture(H, W, seed=4); mask = s.iid_mask(H, W, 1000, 0.10)
 di, dm, do = ctx.to_device(img), ctx.to_device(mask), ctx.alloc(W * H * 3)
 for m in (p.INPAINT_NS, p.INPAINT_TELEA):
