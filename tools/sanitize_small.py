@@ -18,5 +18,14 @@ for m in (p.INPAINT_NS, p.INPAINT_TELEA):
 ctx.watershed(img, s.seed_markers(60, 80, 5, 5))
 rgba = np.random.default_rng(0).random((33, 47, 4), dtype=np.float32)
 ctx.rgba32f_to_srgb_gray8(rgba); ctx.rgba32f_to_srgb8_packed(rgba, 4); ctx.srgb8_packed_to_rgba32f((rgba * 255).astype(np.uint8))
+for (h, w) in ((20, 18), (61, 97), (130, 300)):
+    a, b = s.flow_pair(h, w, seed=4)
+    f, it = ctx.tvl1(a, b, p.Tvl1Params(nscales=3, warps=2, iterations=4, outer_iterations=2))
+    assert np.isfinite(f).all() and it > 0
+r8 = (np.random.default_rng(1).random((36, 48, 4)) * 255).astype(np.uint8)   # widths that take the 4-pixel kernels
+ctx.rgba8_to_rgb8_mask(r8, 2); ctx.rgb8_to_rgba8(np.ascontiguousarray(r8[..., :3]))
+ctx.rgb8_to_rgba8_noise(np.ascontiguousarray(r8[..., :3]), (r8[..., 0] > 200).astype(np.uint8) * 255, 2, 5)
+rg = np.random.default_rng(2).random((9, 260, 4), dtype=np.float32)
+ctx.rgba32f_to_srgb_gray8(rg); ctx.rgba32f_to_srgb8_packed(rg, 4); ctx.srgb8_packed_to_rgba32f((rg * 255).astype(np.uint8))
 ctx.close()
 print("sanitize_small: done")
