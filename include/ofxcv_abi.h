@@ -173,7 +173,9 @@ OFXCV_API size_t ofxcv_tvl1_workspace_bytes(int W, int H, const ofxcv_tvl1_param
  * (in: warped-gradient plane 16 + flow 8 + dual variable 16; out: flow 8 + dual variable 16). */
 OFXCV_API double ofxcv_tvl1_iter_bytes(int W, int H);
 /* prev/next: 8-bit gray, `stride` bytes per row; flow: interleaved (dx,dy) float32, `flow_stride` BYTES/row, rows
- * 8-byte aligned.  Asynchronous on `stream` like ofxcv_farneback_u8; the convergence test stays on the device. */
+ * 8-byte aligned.  The convergence test stays on the device; the host only paces its launches by it (it waits for the
+ * flag of outer iteration n-2 before enqueuing n), so the call returns once the last outer iteration is enqueued --
+ * the tail of the work is still asynchronous on `stream`, like ofxcv_farneback_u8. */
 OFXCV_API int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, const uint8_t* next, ptrdiff_t stride,
                             int W, int H, float* flow, ptrdiff_t flow_stride, const ofxcv_tvl1_params* params);
 /* inner iterations the last ofxcv_tvl1_u8 of this context actually ran (synchronises the device); -1 if none */

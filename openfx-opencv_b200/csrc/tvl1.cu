@@ -489,10 +489,11 @@ int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, cons
     auto I1 = [&](int k) { return (float*)(base + pl.off_i1[k]); };
     auto grid = [](int w, int h) { return dim3(ofxcv_div_up(w, 256), h); };
 
-    // The convergence flag lives on the device; the host only PEEKS at it: after every outer iteration the flag is copied
-    // to pinned memory behind an event, and before enqueuing more work the host looks at the copies whose events have
-    // already completed.  A warping that has stopped then costs no further (no-op) launches when the host is the
-    // bottleneck, and nothing changes when the GPU is: the launches that are skipped would have returned at once.
+    // The convergence flag lives on the device and the launches of a stopped warping return at once, but thousands of
+    // no-op launches still cost microseconds each.  The host therefore paces itself: after every outer iteration the
+    // flag is copied to pinned memory behind an event, and before enqueuing outer iteration n it waits for the copy
+    // made after n-2.  The GPU always has a full outer iteration queued while the host waits, and a stopped warping
+    // wastes at most the rest of that outer iteration and the next one.
     constexpr int TV_NEV = 16;
     int* h_stop = (int*)ofxcv_pin(ctx, 12, TV_NEV * sizeof(int));
     if (!h_stop) return OFXCV_ERR_MEMORY;
@@ -543,18 +544,12 @@ int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, cons
                 tv_warp<<<g, 256, 0, s>>>(J, Ua, Ub, I0(k), A, w, h, ctrl);
                 OFXCV_LAUNCH_CHECK(ctx);
             }
-            int it = 0, ev_head = 0, ev_tail = 0;  // flag copies of THIS warping still in flight: [ev_head, ev_tail)
-            bool stopped = false;
-            auto peek = [&]() {
-                while (ev_head < ev_tail && cudaEventQuery(ctx->tv_ev[ev_head % TV_NEV]) == cudaSuccess) {
-                    if (h_stop[ev_head % TV_NEV] != INT_MAX) stopped = true;
-                    ev_head++;
-                }
-                cudaGetLastError();  // cudaErrorNotReady is not an error
-            };
+            int it = 0;
             for (int no = 0; no < P.outer_iterations; no++) {
-                peek();
-                if (stopped) break;
+                if (no >= 2) {
+                    OFXCV_CUDA(ctx, cudaEventSynchronize(ctx->tv_ev[(no - 2) % TV_NEV]));
+                    if (h_stop[(no - 2) % TV_NEV] != INT_MAX) break;  // everything still queued returns at once
+                }
                 if (P.median_filtering > 1) {
                     ofxcv_prof_scope ps(ctx, s, "tv_median5", k);
                     tv_median5<<<g, 256, 0, s>>>(Ua, Ub, w, h, it, ctrl);
@@ -571,11 +566,10 @@ int ofxcv_tvl1_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, cons
                     OFXCV_LAUNCH_CHECK(ctx);
                     if (timed) ofxcv_time_end(ctx, 1, s);
                 }
-                if (ev_tail - ev_head < TV_NEV && no + 1 < P.outer_iterations) {
-                    const int slot = ev_tail % TV_NEV;
+                if (no + 2 < P.outer_iterations) {
+                    const int slot = no % TV_NEV;
                     OFXCV_CUDA(ctx, cudaMemcpyAsync(&h_stop[slot], &ctrl->stop_at, sizeof(int), cudaMemcpyDeviceToHost, s));
                     OFXCV_CUDA(ctx, cudaEventRecord(ctx->tv_ev[slot], s));
-                    ev_tail++;
                 }
             }
         }
