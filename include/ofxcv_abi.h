@@ -199,6 +199,20 @@ OFXCV_API size_t ofxcv_inpaint_workspace_bytes(int W, int H, int channels);
  * A sequence renderer runs several frames at once (one context + host thread each) and gives every context a share
  * of the SMs: persistent fill CTAs per SM for this context, 1..8 (default 8 = the whole GPU for one frame). */
 OFXCV_API void ofxcv_inpaint_set_fill_blocks(ofxcv_ctx* ctx, int blocks_per_sm);
+/* A clip of independent frames (BASELINE.json config 4 is a 300-frame sequence), `frames_in_flight` of them at a time
+ * (1..8, <= 0 = 8): the library runs one worker (own stream, workspaces and host thread) per frame in flight and splits
+ * the persistent fill CTAs between them -- what a sequence renderer built on ofxcv_inpaint_set_fill_blocks would do
+ * by hand.  imgs / masks / outs: arrays of `nframes` frame pointers with common strides (device pointers; host pointers
+ * for _host, whose uploads and downloads overlap the other frames' compute).  Blocking: waits for `stream`, returns
+ * when every frame is done.  Results are those of ofxcv_inpaint_u8 frame by frame. */
+OFXCV_API int ofxcv_inpaint_sequence_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* const* imgs,
+                                        ptrdiff_t img_stride, int channels, const uint8_t* const* masks,
+                                        ptrdiff_t mask_stride, uint8_t* const* outs, ptrdiff_t out_stride, int W, int H,
+                                        int nframes, double radius, int method, int frames_in_flight);
+OFXCV_API int ofxcv_inpaint_sequence_u8_host(ofxcv_ctx* ctx, const uint8_t* const* imgs, ptrdiff_t img_stride,
+                                             int channels, const uint8_t* const* masks, ptrdiff_t mask_stride,
+                                             uint8_t* const* outs, ptrdiff_t out_stride, int W, int H, int nframes,
+                                             double radius, int method, int frames_in_flight);
 /* statistics of the last inpaint call on ctx: [0]=hole pixels, [1]=marching batches (0.7-wide T windows popped
  * in parallel), [2]=T relaxation rounds over all batches, [3]=kernel launches of the call */
 OFXCV_API int ofxcv_inpaint_last_stats(const ofxcv_ctx* ctx, int64_t stats[4]);

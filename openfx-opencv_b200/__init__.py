@@ -123,6 +123,8 @@ def lib():
         "ofxcv_farneback_sequence_u8_host": (i, [vp, C.POINTER(vp), pd, i, i, i, C.POINTER(vp), pd, fbp]),
         "ofxcv_inpaint_u8": (i, [vp, vp, vp, pd, i, vp, pd, vp, pd, i, i, d, i]),
         "ofxcv_inpaint_u8_host": (i, [vp, vp, pd, i, vp, pd, vp, pd, i, i, d, i]),
+        "ofxcv_inpaint_sequence_u8": (i, [vp, vp, vp, pd, i, vp, pd, vp, pd, i, i, i, d, i, i]),
+        "ofxcv_inpaint_sequence_u8_host": (i, [vp, vp, pd, i, vp, pd, vp, pd, i, i, i, d, i, i]),
         "ofxcv_inpaint_workspace_bytes": (sz, [i, i, i]),
         "ofxcv_inpaint_set_fill_blocks": (None, [vp, i]),
         "ofxcv_inpaint_last_stats": (i, [vp, C.POINTER(C.c_int64)]),
@@ -322,6 +324,33 @@ class Context:
         st = lib().ofxcv_inpaint_u8_host(self.h, _hp(img), w * cn, cn, _hp(mask), w, _hp(out), w * cn, w, h, float(radius), int(method))
         self._check(st, "ofxcv_inpaint_u8_host")
         return out
+
+    def inpaint_sequence(self, imgs, masks, radius, method, frames_in_flight=0):
+        """A clip of independent frames (host arrays), several in flight (ofxcv_inpaint_sequence_u8_host)."""
+        imgs = [np.ascontiguousarray(a, np.uint8) for a in imgs]
+        masks = [np.ascontiguousarray(m, np.uint8) for m in masks]
+        if not imgs:
+            return []
+        if len(imgs) != len(masks):
+            raise ValueError("one mask per frame")
+        h, w = masks[0].shape
+        cn = 1 if imgs[0].ndim == 2 else imgs[0].shape[2]
+        if any(a.shape != imgs[0].shape for a in imgs) or any(m.shape != (h, w) for m in masks) or imgs[0].shape[:2] != (h, w):
+            raise ValueError("all frames and masks of a clip must have the same size")
+        outs = [np.empty_like(a) for a in imgs]
+        n = len(imgs)
+        arr = lambda xs: (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+        st = lib().ofxcv_inpaint_sequence_u8_host(self.h, arr(imgs), w * cn, cn, arr(masks), w, arr(outs), w * cn, w, h, n, float(radius),
+                                                  int(method), int(frames_in_flight))
+        self._check(st, "ofxcv_inpaint_sequence_u8_host")
+        return outs
+
+    def inpaint_sequence_dev(self, img_ptrs, cn, mask_ptrs, out_ptrs, w, h, radius, method, frames_in_flight=0, stream=None):
+        n = len(img_ptrs)
+        arr = lambda xs: (C.c_void_p * n)(*xs)
+        st = lib().ofxcv_inpaint_sequence_u8(self.h, stream, arr(img_ptrs), w * cn, cn, arr(mask_ptrs), w, arr(out_ptrs), w * cn, w, h, n,
+                                             float(radius), int(method), int(frames_in_flight))
+        self._check(st, "ofxcv_inpaint_sequence_u8")
 
     def inpaint_set_fill_blocks(self, blocks_per_sm):
         lib().ofxcv_inpaint_set_fill_blocks(self.h, int(blocks_per_sm))

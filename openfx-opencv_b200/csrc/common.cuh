@@ -64,6 +64,7 @@ struct ofxcv_ctx {
     cudaStream_t stream_up = nullptr, stream_down = nullptr, stream_lane[2] = {nullptr, nullptr};
     cudaEvent_t lane_done[2] = {nullptr, nullptr}, lane_start = nullptr;
     cudaEvent_t seq_ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    ofxcv_ctx* sub[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // workers of ofxcv_inpaint_sequence_u8 (owned)
     int ip_fill_blocks_per_sm = 8;  // persistent CTAs of the inpaint fill kernel per SM (ofxcv_inpaint_set_fill_blocks)
     cudaEvent_t tv_ev[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t tv_ctrl_off = 0;  // where the last ofxcv_tvl1_u8 put its control block inside WS_TV_ARENA

@@ -124,6 +124,10 @@ ofxcv_ctx* ofxcv_create(int device)
 void ofxcv_destroy(ofxcv_ctx* ctx)
 {
     if (!ctx) return;
+    for (auto& c : ctx->sub) {
+        if (c) ofxcv_destroy(c);
+        c = nullptr;
+    }
     ofxcv_device_guard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->ws)

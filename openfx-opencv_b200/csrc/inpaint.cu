@@ -21,6 +21,10 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <thread>
+#include <vector>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -1184,6 +1188,74 @@ int ofxcv_inpaint_u8_host(ofxcv_ctx* ctx, const uint8_t* img, ptrdiff_t img_stri
     OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
     for (int y = 0; y < H; y++) memcpy(out + (size_t)y * out_stride, ho + (size_t)y * rb, rb);
     return OFXCV_OK;
+}
+
+// A clip of independent frames, several in flight: worker k (own sub-context = own stream and workspaces, own host
+// thread because the marching reads its batch counters back) takes frames k, k+K, ...; the persistent fill CTAs of
+// the K frames share the SMs.  Blocking: waits for `stream`, returns when every frame is done.
+static int ip_sequence(ofxcv_ctx* ctx, ofxcv_stream stream, bool host, const uint8_t* const* imgs, ptrdiff_t img_stride, int channels,
+                       const uint8_t* const* masks, ptrdiff_t mask_stride, uint8_t* const* outs, ptrdiff_t out_stride, int W, int H,
+                       int nframes, double radius, int method, int frames_in_flight)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!imgs || !masks || !outs || nframes < 0) return OFXCV_ERR_BAD_ARG;
+    if (nframes == 0) return OFXCV_OK;
+    for (int f = 0; f < nframes; f++)
+        if (!imgs[f] || !masks[f] || !outs[f]) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard guard(ctx->device);
+    OFXCV_CUDA(ctx, cudaStreamSynchronize(stream ? (cudaStream_t)stream : ctx->stream));
+    int K = frames_in_flight <= 0 ? 8 : frames_in_flight;
+    K = std::min(std::min(K, 8), nframes);
+    for (int k = 0; k < K; k++) {
+        if (!ctx->sub[k]) ctx->sub[k] = ofxcv_create(ctx->device);
+        if (!ctx->sub[k]) return OFXCV_ERR_MEMORY;
+        ofxcv_inpaint_set_fill_blocks(ctx->sub[k], std::max(1, 8 / K));
+    }
+    std::vector<int> status(K, OFXCV_OK);
+    std::vector<int64_t> holes(K, 0), launches(K, 0);
+    auto work = [&](int k) {
+        ofxcv_ctx* c = ctx->sub[k];
+        cudaSetDevice(ctx->device);
+        for (int f = k; f < nframes && status[k] == OFXCV_OK; f += K) {
+            status[k] = host ? ofxcv_inpaint_u8_host(c, imgs[f], img_stride, channels, masks[f], mask_stride, outs[f], out_stride, W, H, radius, method)
+                             : ofxcv_inpaint_u8(c, nullptr, imgs[f], img_stride, channels, masks[f], mask_stride, outs[f], out_stride, W, H, radius,
+                                                method);
+            holes[k] += c->inpaint_stats[0];
+            launches[k] += c->inpaint_stats[3];
+        }
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess && status[k] == OFXCV_OK) status[k] = OFXCV_ERR_CUDA;
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < K; k++) th.emplace_back(work, k);
+    work(0);
+    for (auto& t : th) t.join();
+    ctx->inpaint_stats[0] = ctx->inpaint_stats[1] = ctx->inpaint_stats[2] = ctx->inpaint_stats[3] = 0;
+    for (int k = 0; k < K; k++) {
+        ctx->inpaint_stats[0] += holes[k];
+        ctx->inpaint_stats[3] += launches[k];
+        ctx->launches += (uint64_t)launches[k];
+        if (status[k] != OFXCV_OK) {
+            ctx->last_error = ctx->sub[k]->last_error;
+            return status[k];
+        }
+    }
+    return OFXCV_OK;
+}
+
+int ofxcv_inpaint_sequence_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* const* imgs, ptrdiff_t img_stride, int channels,
+                              const uint8_t* const* masks, ptrdiff_t mask_stride, uint8_t* const* outs, ptrdiff_t out_stride, int W, int H,
+                              int nframes, double radius, int method, int frames_in_flight)
+{
+    return ip_sequence(ctx, stream, false, imgs, img_stride, channels, masks, mask_stride, outs, out_stride, W, H, nframes, radius, method,
+                       frames_in_flight);
+}
+
+int ofxcv_inpaint_sequence_u8_host(ofxcv_ctx* ctx, const uint8_t* const* imgs, ptrdiff_t img_stride, int channels,
+                                   const uint8_t* const* masks, ptrdiff_t mask_stride, uint8_t* const* outs, ptrdiff_t out_stride, int W,
+                                   int H, int nframes, double radius, int method, int frames_in_flight)
+{
+    return ip_sequence(ctx, nullptr, true, imgs, img_stride, channels, masks, mask_stride, outs, out_stride, W, H, nframes, radius, method,
+                       frames_in_flight);
 }
 
 }  // extern "C"

@@ -87,3 +87,25 @@ def flow_clip(ctx, load_frame, n_frames, params=None, world=None, rank=None, kee
     for part in gather_results(mine):
         merged.update(dict(part))
     return first, (flows if keep else None), [merged[i] for i in range(n_frames - 1)]
+
+
+def inpaint_clip(ctx, load_frame, n_frames, radius, method, world=None, rank=None, keep=True, frames_in_flight=0):
+    """Inpaint a whole clip, frame-sharded over the ranks of the default process group (BASELINE.json config 4).
+
+    load_frame(t) -> (HxWx3 or HxW uint8 image, HxW uint8 mask) is called only for this rank's contiguous block; the
+    block goes through ONE clip call of the C ABI (ofxcv_inpaint_sequence_u8_host: several frames in flight).  Returns
+    (first, frames or None, checksums of ALL n_frames outputs in clip order, gathered from every rank)."""
+    import torch.distributed as dist
+    inited = dist.is_available() and dist.is_initialized()
+    world = world if world is not None else (dist.get_world_size() if inited else 1)
+    rank = rank if rank is not None else (dist.get_rank() if inited else 0)
+    first, count = shard_range(n_frames, world, rank)
+    pairs = [load_frame(t) for t in range(first, first + count)]
+    if inited:
+        dist.barrier()
+    outs = ctx.inpaint_sequence([p[0] for p in pairs], [p[1] for p in pairs], radius, method, frames_in_flight) if count else []
+    mine = [(first + i, checksum64(o)) for i, o in enumerate(outs)]
+    merged = {}
+    for part in gather_results(mine):
+        merged.update(dict(part))
+    return first, (outs if keep else None), [merged[i] for i in range(n_frames)]

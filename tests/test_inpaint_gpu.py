@@ -118,3 +118,23 @@ def test_inpaint_both_schedulers(ctx, oracle, synth, method, sched, monkeypatch)
             got = ctx.inpaint(img, mask, radius, method)
             ref = oracle.inpaint(img, mask, radius, method)
             assert np.array_equal(got, ref), "%s r=%d scheduler %s: %d differing bytes" % (name, radius, sched, int((got != ref).sum()))
+
+
+def test_inpaint_clip_equals_frame_by_frame(pkg, ctx, oracle, synth):
+    """ofxcv_inpaint_sequence_u8[_host]: several frames in flight on worker sub-contexts give the bits of one frame
+    at a time (and of the oracle), for every in-flight count incl. more workers than frames."""
+    h, w = 72, 96
+    imgs = [synth.texture(h, w, 30 + f) for f in range(5)]
+    masks = [synth.iid_mask(h, w, 40 + f, 0.05 + 0.03 * f) for f in range(4)] + [np.zeros((h, w), np.uint8)]   # last: nothing to do
+    for method in (pkg.INPAINT_NS, pkg.INPAINT_TELEA):
+        ref = [oracle.inpaint(a, m, 3, method) for a, m in zip(imgs, masks)]
+        for k in (0, 1, 3, 8):
+            outs = ctx.inpaint_sequence(imgs, masks, 3, method, frames_in_flight=k)
+            assert all(np.array_equal(o, r) for o, r in zip(outs, ref)), (method, k)
+    # device-pointer flavour
+    di = [ctx.to_device(a) for a in imgs]; dm = [ctx.to_device(m) for m in masks]; do = [ctx.alloc(h * w * 3) for _ in imgs]
+    ctx.inpaint_sequence_dev([b.ptr for b in di], 3, [b.ptr for b in dm], [b.ptr for b in do], w, h, 3.0, pkg.INPAINT_TELEA, 2)
+    ref = [oracle.inpaint(a, m, 3, pkg.INPAINT_TELEA) for a, m in zip(imgs, masks)]
+    assert all(np.array_equal(b.download((h, w, 3), np.uint8), r) for b, r in zip(do, ref))
+    assert ctx.inpaint_sequence([], [], 3, 0) == []
+    assert ctx.inpaint_stats()["hole_pixels"] == sum(int((m != 0).sum()) for m in masks)

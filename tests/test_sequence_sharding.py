@@ -74,6 +74,50 @@ class _FakeCtx:
         return [np.stack([b.astype(np.float32) - a, a.astype(np.float32)], axis=-1) for a, b in zip(frames[:-1], frames[1:])]
 
 
+class _FakeInpaintCtx:
+    def inpaint_sequence(self, imgs, masks, radius, method, frames_in_flight=0):
+        return [np.where(m[..., None] != 0, 255 - a, a).astype(np.uint8) for a, m in zip(imgs, masks)]
+
+
+def _inpaint_clip_worker(rank, world, port, n_frames, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    loaded = []
+
+    def load(t):
+        loaded.append(t)
+        return np.full((4, 6, 3), 10 * t, np.uint8), (np.arange(24).reshape(4, 6) % (t + 2) == 0).astype(np.uint8)
+
+    first, outs, sums = seq.inpaint_clip(_FakeInpaintCtx(), load, n_frames, 3.0, 0)
+    q.put((rank, first, loaded, len(outs), sums))
+    dist.destroy_process_group()
+
+
+def test_inpaint_clip_gloo_world2():
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_frames, world, port = 5, 2, 29717 + os.getpid() % 1000
+    procs = [ctx.Process(target=_inpaint_clip_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=100) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    fake = _FakeInpaintCtx()
+    expect = []
+    for t in range(n_frames):
+        a, m = np.full((4, 6, 3), 10 * t, np.uint8), (np.arange(24).reshape(4, 6) % (t + 2) == 0).astype(np.uint8)
+        expect.append(seq.checksum64(fake.inpaint_sequence([a], [m], 3.0, 0)[0]))
+    (r0, f0, l0, n0, s0), (r1, f1, l1, n1, s1) = outs
+    assert (f0, n0, l0) == (0, 3, [0, 1, 2]) and (f1, n1, l1) == (3, 2, [3, 4])   # contiguous blocks, no halo
+    assert s0 == expect and s1 == expect
+
+
 def _clip_worker(rank, world, port, n_frames, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
