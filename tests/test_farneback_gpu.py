@@ -184,3 +184,20 @@ def test_flow_clip_driver_single_rank(ctx, pkg, synth):
     for t in range(n - 1):
         ref = ctx.farneback(synth.shift_bilinear(base, 1.0 * t, 0.5 * t), synth.shift_bilinear(base, 1.0 * (t + 1), 0.5 * (t + 1)), p)
         assert np.array_equal(flows[t], ref) and sums[t] == seq.checksum64(ref)
+
+
+def test_farneback_c5_8k_levels5_properties(ctx, pkg, synth):
+    """BASELINE.json config 5's frame (7680x4320 Texture(seed 2000) shifted by (2.5, -1.5) px, levels = 5 -> 6 scales):
+    the oracle would take minutes, so size-independent properties: the known translation is recovered as well as at 4K,
+    two runs are bit-identical."""
+    h, w = 4320, 7680
+    par = pkg.FbParams(levels=5)
+    assert pkg.lib().ofxcv_farneback_scales(w, h, par) == 6
+    base = synth.gray(synth.texture(h, w, seed=2000))
+    nxt = synth.shift_bilinear(base, 2.5, -1.5)
+    a = ctx.farneback(base, nxt, par)
+    b = ctx.farneback(base, nxt, par)
+    assert np.array_equal(a, b) and np.isfinite(a).all()
+    c = a[400:-400, 400:-400]
+    epe = np.hypot(c[..., 0] - 2.5, c[..., 1] + 1.5)
+    assert epe.mean() < 0.5 and np.median(epe) < 0.3, (epe.mean(), np.median(epe))

@@ -138,3 +138,13 @@ def test_inpaint_clip_equals_frame_by_frame(pkg, ctx, oracle, synth):
     assert all(np.array_equal(b.download((h, w, 3), np.uint8), r) for b, r in zip(do, ref))
     assert ctx.inpaint_sequence([], [], 3, 0) == []
     assert ctx.inpaint_stats()["hole_pixels"] == sum(int((m != 0).sum()) for m in masks)
+
+
+def test_inpaint_c4_4k_ns_10pct(ctx, oracle, synth):
+    """BASELINE.json config 4's frame: 3840x2160 RGB8, 10 % iid mask, radius 3, Navier-Stokes — 0 differing bytes."""
+    img = synth.texture(2160, 3840, 100)
+    mask = synth.iid_mask(2160, 3840, 1000, 0.10)
+    got = ctx.inpaint(img, mask, 3, NS)
+    ref = oracle.inpaint(img, mask, 3, NS)
+    assert int((got != ref).sum()) == 0
+    assert np.array_equal(got[mask == 0], img[mask == 0])

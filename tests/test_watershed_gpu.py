@@ -35,3 +35,16 @@ def test_watershed_no_seeds(ctx, oracle):
     got = ctx.watershed(img, mk)
     ref, _ = oracle.watershed(img, mk)
     assert np.array_equal(got, ref)
+
+
+def test_watershed_c3_4k_256_seeds(ctx, oracle, synth):
+    """BASELINE.json config 3 itself: 3840x2160, 256 seed markers — the whole int32 label map equals the oracle's
+    (which equals cv2.watershed on this very input: tests/golden + SURVEY A.3), pop count included."""
+    h, w = 2160, 3840
+    img = synth.texture(h, w, 4)
+    mk = synth.seed_markers(h, w, 256, 5)
+    got = ctx.watershed(img, mk)
+    ref, pops = oracle.watershed(img, mk)
+    assert np.array_equal(got, ref)
+    assert ctx.watershed_stats()["pops"] == pops
+    assert (got[0] == -1).all() and (got[:, 0] == -1).all() and set(np.unique(got)) <= set(range(-1, 257)) and (got != 0).all()
