@@ -378,6 +378,31 @@ class Context:
         self._check(st, "ofxcv_watershed_u8c3_host")
         return m
 
+    def watershed_sequence(self, rgbs, markers):
+        """A clip of independent frames flooded concurrently (ofxcv_watershed_u8c3_batch): lists of HxWx3 uint8 frames and
+        HxW int32 marker maps -> list of label maps."""
+        n = len(rgbs)
+        if n == 0:
+            return []
+        if len(markers) != n:
+            raise ValueError("one marker map per frame")
+        h, w = np.asarray(markers[0]).shape
+        d_rgb, d_mk = self.alloc(w * h * 3 * n), self.alloc(w * h * 4 * n)
+        try:
+            for f in range(n):
+                a = np.ascontiguousarray(rgbs[f], np.uint8)
+                m = np.ascontiguousarray(markers[f], np.int32)
+                if a.shape != (h, w, 3) or m.shape != (h, w):
+                    raise ValueError("all frames and marker maps of a clip must have the same size")
+                self._check(lib().ofxcv_upload(self.h, None, d_rgb.ptr + f * w * h * 3, _hp(a), w * h * 3), "ofxcv_upload")
+                self._check(lib().ofxcv_upload(self.h, None, d_mk.ptr + f * w * h * 4, _hp(m), w * h * 4), "ofxcv_upload")
+                self.synchronize()   # `a` / `m` may be temporaries
+            self.watershed_dev(d_rgb.ptr, d_mk.ptr, w, h, n)
+            out = d_mk.download((n, h, w), np.int32)
+        finally:
+            d_rgb.free(); d_mk.free()
+        return [out[f] for f in range(n)]
+
     def watershed_stats(self):
         s = (C.c_int64 * 4)()
         self._check(lib().ofxcv_watershed_last_stats(self.h, s), "ofxcv_watershed_last_stats")

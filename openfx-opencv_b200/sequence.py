@@ -109,3 +109,29 @@ def inpaint_clip(ctx, load_frame, n_frames, radius, method, world=None, rank=Non
     for part in gather_results(mine):
         merged.update(dict(part))
     return first, (outs if keep else None), [merged[i] for i in range(n_frames)]
+
+
+def watershed_clip(ctx, load_frame, n_frames, world=None, rank=None, keep=True, frames_in_flight=128):
+    """Watershed of a whole clip, frame-sharded over the ranks of the default process group.
+
+    load_frame(t) -> (HxWx3 uint8 image, HxW int32 markers), called only for this rank's contiguous block; the block is
+    flooded `frames_in_flight` frames at a time (ofxcv_watershed_u8c3_batch — the exact flood is sequential per frame, a
+    clip's throughput comes from frames in flight).  Returns (first, label maps or None, checksums of ALL frames)."""
+    import torch.distributed as dist
+    inited = dist.is_available() and dist.is_initialized()
+    world = world if world is not None else (dist.get_world_size() if inited else 1)
+    rank = rank if rank is not None else (dist.get_rank() if inited else 0)
+    first, count = shard_range(n_frames, world, rank)
+    if inited:
+        dist.barrier()
+    outs, sums = [], []
+    for lo in range(first, first + count, max(1, frames_in_flight)):
+        pairs = [load_frame(t) for t in range(lo, min(lo + max(1, frames_in_flight), first + count))]
+        labs = ctx.watershed_sequence([p[0] for p in pairs], [p[1] for p in pairs])
+        sums += [(lo + i, checksum64(l)) for i, l in enumerate(labs)]
+        if keep:
+            outs += labs
+    merged = {}
+    for part in gather_results(sums):
+        merged.update(dict(part))
+    return first, (outs if keep else None), [merged.get(i) for i in range(n_frames)]   # None: owned by a rank outside the group

@@ -74,6 +74,26 @@ class _FakeCtx:
         return [np.stack([b.astype(np.float32) - a, a.astype(np.float32)], axis=-1) for a, b in zip(frames[:-1], frames[1:])]
 
 
+class _FakeWatershedCtx:
+    def __init__(self):
+        self.batches = []
+
+    def watershed_sequence(self, rgbs, markers):
+        self.batches.append(len(rgbs))
+        return [np.where(m > 0, m, -1).astype(np.int32) for m in markers]
+
+
+def test_watershed_clip_batches_and_order():
+    """Host logic of the watershed clip driver on one rank: contiguous block, frames_in_flight-sized batches."""
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    fake = _FakeWatershedCtx()
+    frames = [(np.zeros((3, 4, 3), np.uint8), np.full((3, 4), t % 3, np.int32)) for t in range(10)]
+    first, labs, sums = seq.watershed_clip(fake, lambda t: frames[t], 10, world=2, rank=1, frames_in_flight=2)
+    assert first == 5 and fake.batches == [2, 2, 1] and len(labs) == 5
+    assert sums[:5] == [None] * 5   # no process group here: the other rank's checksums are not gathered
+    assert sums[5:] == [seq.checksum64(np.where(frames[t][1] > 0, frames[t][1], -1).astype(np.int32)) for t in range(5, 10)]
+
+
 class _FakeInpaintCtx:
     def inpaint_sequence(self, imgs, masks, radius, method, frames_in_flight=0):
         return [np.where(m[..., None] != 0, 255 - a, a).astype(np.uint8) for a, m in zip(imgs, masks)]

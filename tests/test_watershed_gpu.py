@@ -48,3 +48,16 @@ def test_watershed_c3_4k_256_seeds(ctx, oracle, synth):
     assert np.array_equal(got, ref)
     assert ctx.watershed_stats()["pops"] == pops
     assert (got[0] == -1).all() and (got[:, 0] == -1).all() and set(np.unique(got)) <= set(range(-1, 257)) and (got != 0).all()
+
+
+def test_watershed_clip_equals_frame_by_frame(pkg, ctx, oracle, synth):
+    """Frames in flight (ofxcv_watershed_u8c3_batch through the clip driver) give each frame's own label map."""
+    import importlib
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    h, w = 60, 84
+    frames = [(synth.texture(h, w, 50 + f), synth.seed_markers(h, w, 4 + f, 60 + f)) for f in range(7)]
+    first, labs, sums = seq.watershed_clip(ctx, lambda t: frames[t], len(frames), frames_in_flight=3)
+    assert first == 0 and len(labs) == 7
+    for (img, mk), lab, cs in zip(frames, labs, sums):
+        ref, _ = oracle.watershed(img, mk)
+        assert np.array_equal(lab, ref) and cs == seq.checksum64(ref)
