@@ -306,6 +306,15 @@ __global__ void __launch_bounds__(32) ws_flood2(int32_t* __restrict__ m, ptrdiff
     pops_out[f] = pops;
 }
 
+// Measured and rejected on top of ws_flood2 (3840x2160, 256 seeds: 3.7 s, 187 instructions and ~830 cycles per pop, of
+// which ncu attributes 35 % to memory and the rest to issue + dependent-ALU latency of the one warp):
+//  * warming L1 for queued pixels -- `prefetch.global.L1` does not allocate in L1 on sm_100a, a 4-byte cp.async.ca into
+//    a shared-memory sink does (tools/microbench/l1_prefetch.cu: 470 vs 39 cycles per dependent load), but the 20+
+//    extra instructions per push cost more than the misses they remove: 6.0 s;
+//  * one warp per frame with lanes 1-4 owning the four neighbours (label rule = two ballots, same-level pushes linked
+//    in lane order, level scan by ballot): bit-identical, but every cross-lane step (shuffle, ballot, __syncwarp,
+//    shared-memory hand-off) has a longer dependent latency than the scalar code it replaces: 5.2 s.
+
 }  // namespace
 
 extern "C" {
