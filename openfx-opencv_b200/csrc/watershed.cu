@@ -252,11 +252,15 @@ __global__ void __launch_bounds__(32) ws_flood2(int32_t* __restrict__ m, ptrdiff
             if (mu > 0) { if (lab == 0) lab = mu; else if (mu != lab) lab = WS_WSHED; }
             if (md > 0) { if (lab == 0) lab = md; else if (md != lab) lab = WS_WSHED; }
             mf[p] = lab;
+            // the prefetched registers need patching only when the predicted pixel lies within two rows of p
+            const bool near = (unsigned)(pn - p + 2 * ms + 2) <= (unsigned)(4 * ms + 4);
             // p's label as seen by the prefetched pixel
-            if (pn - 1 == p) nl = lab;
-            if (pn + 1 == p) nr = lab;
-            if (pn - ms == p) nu = lab;
-            if (pn + ms == p) nd = lab;
+            if (near) {
+                if (pn - 1 == p) nl = lab;
+                if (pn + 1 == p) nr = lab;
+                if (pn - ms == p) nu = lab;
+                if (pn + ms == p) nd = lab;
+            }
             const int level_at_pop = active;
             if (lab != WS_WSHED) {
 #define WS_PUSH2(cond, q, cq)                                        \
@@ -271,10 +275,12 @@ __global__ void __launch_bounds__(32) ws_flood2(int32_t* __restrict__ m, ptrdiff
         tail[t] = (q);                                               \
         if (t < active) active = t;                                  \
         mf[q] = WS_IN_QUEUE;                                         \
-        if (pn - 1 == (q)) nl = WS_IN_QUEUE;                         \
-        if (pn + 1 == (q)) nr = WS_IN_QUEUE;                         \
-        if (pn - ms == (q)) nu = WS_IN_QUEUE;                        \
-        if (pn + ms == (q)) nd = WS_IN_QUEUE;                        \
+        if (near) {                                                  \
+            if (pn - 1 == (q)) nl = WS_IN_QUEUE;                     \
+            if (pn + 1 == (q)) nr = WS_IN_QUEUE;                     \
+            if (pn - ms == (q)) nu = WS_IN_QUEUE;                    \
+            if (pn + ms == (q)) nd = WS_IN_QUEUE;                    \
+        }                                                            \
     }
                 WS_PUSH2(ml == 0, p - 1, cl)
                 WS_PUSH2(mr == 0, p + 1, cr)
