@@ -148,43 +148,34 @@ __global__ void __launch_bounds__(256) tv_warp(const float4* __restrict__ J, con
     A[o] = make_float4(s1, s2, s1 * s1 + s2 * s2, s0 - s1 * u.x - s2 * u.y - I0[o]);
 }
 
-// 5x5 median of both flow components (replicated border) by forgetful selection: keep 14 candidates, drop their
-// minimum and maximum, add the next value, ... until one is left (168 compare-exchanges per component; the median of a
-// multiset does not depend on how it is found).  Passes the flow through unchanged once the warping has stopped, so
-// that the host can swap the two buffers unconditionally.
+// 5x5 median of both flow components (replicated border) through a 99-exchange selection network (the classic
+// median-of-25 network; tests/test_abi.py re-verifies this very list on all 2^25 zero-one inputs, which by the zero-one
+// principle proves it for every input; the median of a multiset does not depend on how it is found).  The launch
+// does nothing once the warping has stopped.
 __device__ __forceinline__ void tv_cswap(float& a, float& b)
 {
     const float lo = fminf(a, b), hi = fmaxf(a, b);
     a = lo;
     b = hi;
 }
-template <int N>
-__device__ __forceinline__ void tv_minmax_to_ends(float (&v)[14])  // minimum to v[0], maximum to v[N-1]
+#define TV_MED25_NET \
+    X(0, 1) X(3, 4) X(2, 4) X(2, 3) X(6, 7) X(5, 7) X(5, 6) X(9, 10) X(8, 10) \
+    X(8, 9) X(12, 13) X(11, 13) X(11, 12) X(15, 16) X(14, 16) X(14, 15) X(18, 19) X(17, 19) \
+    X(17, 18) X(21, 22) X(20, 22) X(20, 21) X(23, 24) X(2, 5) X(3, 6) X(0, 6) X(0, 3) \
+    X(4, 7) X(1, 7) X(1, 4) X(11, 14) X(8, 14) X(8, 11) X(12, 15) X(9, 15) X(9, 12) \
+    X(13, 16) X(10, 16) X(10, 13) X(20, 23) X(17, 23) X(17, 20) X(21, 24) X(18, 24) X(18, 21) \
+    X(19, 22) X(8, 17) X(9, 18) X(0, 18) X(0, 9) X(10, 19) X(1, 19) X(1, 10) X(11, 20) \
+    X(2, 20) X(2, 11) X(12, 21) X(3, 21) X(3, 12) X(13, 22) X(4, 22) X(4, 13) X(14, 23) \
+    X(5, 23) X(5, 14) X(15, 24) X(6, 24) X(6, 15) X(7, 16) X(7, 19) X(13, 21) X(15, 23) \
+    X(7, 13) X(7, 15) X(1, 9) X(3, 11) X(5, 17) X(11, 17) X(9, 17) X(4, 10) X(6, 12) \
+    X(7, 14) X(4, 6) X(4, 7) X(12, 14) X(10, 14) X(6, 7) X(10, 12) X(6, 10) X(6, 17) \
+    X(12, 17) X(7, 17) X(7, 10) X(12, 18) X(7, 12) X(10, 18) X(12, 20) X(10, 20) X(10, 12)
+__device__ __forceinline__ float tv_median25(float (&v)[25])
 {
-#pragma unroll
-    for (int i = 0; i < N - 1; i++) tv_cswap(v[i], v[i + 1]);
-#pragma unroll
-    for (int i = N - 2; i > 0; i--) tv_cswap(v[i - 1], v[i]);
-}
-__device__ __forceinline__ float tv_median25(const float (&a)[25])
-{
-    float v[14];
-#pragma unroll
-    for (int i = 0; i < 14; i++) v[i] = a[i];
-    // after each step the survivors sit in v[1..N-2]; the next value replaces the dropped minimum
-    tv_minmax_to_ends<14>(v); v[0] = a[14];
-    tv_minmax_to_ends<13>(v); v[0] = a[15];
-    tv_minmax_to_ends<12>(v); v[0] = a[16];
-    tv_minmax_to_ends<11>(v); v[0] = a[17];
-    tv_minmax_to_ends<10>(v); v[0] = a[18];
-    tv_minmax_to_ends<9>(v); v[0] = a[19];
-    tv_minmax_to_ends<8>(v); v[0] = a[20];
-    tv_minmax_to_ends<7>(v); v[0] = a[21];
-    tv_minmax_to_ends<6>(v); v[0] = a[22];
-    tv_minmax_to_ends<5>(v); v[0] = a[23];
-    tv_minmax_to_ends<4>(v); v[0] = a[24];
-    tv_minmax_to_ends<3>(v);
-    return v[1];
+#define X(i, j) tv_cswap(v[i], v[j]);
+    TV_MED25_NET
+#undef X
+    return v[12];
 }
 
 __global__ void __launch_bounds__(256) tv_median5(float2* __restrict__ U0, float2* __restrict__ U1, int w, int h, int iter, TvCtrl* __restrict__ ctrl)

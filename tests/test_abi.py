@@ -106,3 +106,25 @@ def test_concurrent_contexts_are_independent(pkg, synth):
     for i in range(4):
         for a, b in zip(results[i], ref):
             assert np.array_equal(a, b)
+
+
+def test_median25_network_is_a_median():
+    """tv_median5 (Dual TV-L1) finds the 5x5 median with a 99-exchange min/max network.  Zero-one principle: a comparator
+    network selects the median of every input iff it does so for all 2^25 inputs of zeros and ones — checked here,
+    bit-parallel, on the exact list compiled into csrc/tvl1.cu."""
+    import numpy as np
+    src = open(os.path.join(ROOT, "openfx-opencv_b200", "csrc", "tvl1.cu")).read()
+    body = src[src.index("#define TV_MED25_NET"):src.index("__device__ __forceinline__ float tv_median25")]
+    pairs = [(int(a), int(b)) for a, b in re.findall(r"X\((\d+), (\d+)\)", body)]
+    assert len(pairs) == 99 and all(0 <= a < b < 25 for a, b in pairs)
+    n = 1 << 25
+    idx = np.arange(n, dtype=np.uint32)
+    wires, ones = [], np.zeros(n, np.uint8)
+    for k in range(25):
+        bit = ((idx >> k) & 1).astype(np.uint8)
+        ones += bit
+        wires.append(np.packbits(bit, bitorder="little").view(np.uint64))
+    for a, b in pairs:
+        wires[a], wires[b] = wires[a] & wires[b], wires[a] | wires[b]     # (min, max)
+    expect = np.packbits((ones >= 13).astype(np.uint8), bitorder="little").view(np.uint64)
+    assert np.array_equal(wires[12], expect)
