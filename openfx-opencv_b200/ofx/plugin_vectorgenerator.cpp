@@ -158,6 +158,7 @@ void stage_gray(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, bool devi
         return;
     }
     if (device_ptrs) throw StatusException{kOfxStatErrUnsupported};
+    check_cv(ofxcv_synchronize(ctx));  // the previous frame's upload out of `stage` must have left the pinned buffer
     float* s = (float*)stage.p;
     const OfxRectI& b = img.bounds;
     for (int y = win.y1; y < win.y2; y++) {
