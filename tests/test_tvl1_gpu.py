@@ -18,6 +18,9 @@ def _pair(synth, h, w, seed, dx=2.5, dy=-1.5):
     ((61, 97), dict(nscales=5, warps=3, iterations=7, outer_iterations=2)),
     ((61, 97), dict(nscales=4, warps=2, iterations=6, outer_iterations=2, median_filtering=1)),
     ((20, 18), dict(nscales=5, warps=2, iterations=4, outer_iterations=2)),          # scales below 16 px are dropped
+    ((5, 7), dict(nscales=3, warps=2, iterations=3, outer_iterations=3)),            # smaller than every window
+    ((1, 40), dict(nscales=2, warps=1, iterations=3, outer_iterations=1)),           # a single row
+    ((37, 1), dict(nscales=2, warps=1, iterations=3, outer_iterations=1)),           # a single column
     ((33, 300), dict(nscales=2, warps=2, iterations=5, outer_iterations=2, tau=0.2, lambda_=0.3, theta=0.25)),
     ((120, 160), dict()),                                                            # the plugin's defaults
 ])
