@@ -159,6 +159,11 @@ void stage_gray(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, bool devi
     }
     if (device_ptrs) throw StatusException{kOfxStatErrUnsupported};
     check_cv(ofxcv_synchronize(ctx));  // the previous frame's upload out of `stage` must have left the pinned buffer
+    if (window_inside(win, img.bounds)) {  // the usual case: row copies by a few workers, overlapped with the H2D copies
+        upload_window(ctx, img, win, nc * 4, (char*)stage.p, d_float.p);
+        check_cv(ofxcv_rgba32f_to_srgb_gray8(ctx, nullptr, (const float*)d_float.p, (ptrdiff_t)W * nc * 4, nc, d_gray, W, W, H));
+        return;
+    }
     float* s = (float*)stage.p;
     const OfxRectI& b = img.bounds;
     for (int y = win.y1; y < win.y2; y++) {
@@ -250,9 +255,7 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
                                        a.scale.y));
     }
     if (!dev) {
-        check_cv(ofxcv_download(ctx, nullptr, stage.p, d_dst.p, n * 16));
-        check_cv(ofxcv_synchronize(ctx));
-        scatter_rows(dst.img, win, 16, (const char*)stage.p);
+        download_window(ctx, dst.img, win, 16, (char*)stage.p, d_dst.p);
     } else {
         check_cv(ofxcv_synchronize(ctx));
     }

@@ -291,3 +291,32 @@ def test_vectorgenerator_cuda_render_handoff(mh, oracle, synth, ctx):
     d = np.abs(got[..., :2] - ref).max(axis=2)
     assert d.mean() <= 1e-3 and not got[..., 2:].any()
     p.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flip", [False, True])
+def test_vectorgenerator_plugin_large_host_images(mh, pkg, ctx, oracle, synth, flip):
+    """1080p host-memory clips take the chunked staging path of the glue (worker threads copy row chunks into pinned
+    memory while the H2D copies run; the result is scattered by the workers): the render must equal the C ABI called
+    directly on the same frames, with bottom-up and top-down (negative rowBytes) host images."""
+    h, w = 1080, 1920
+    base = synth.gray(synth.texture(h, w, 31))
+    gray = {t: synth.shift_bilinear(base, 1.5 * t, -0.75 * t) for t in (0, 1)}
+    frames = {t: _float_rgba(synth, oracle, g) for t, g in gray.items()}
+    p = mh.Plugin("VectorGenerator")
+    assert p.create_instance() == 0
+    for n, v in (("rChannel", 1), ("gChannel", 2), ("bChannel", 0), ("aChannel", 0), ("levels", 2), ("iterations", 3)):
+        p.set_param(n, v)
+    for t, f in frames.items():
+        p.set_image("Source", t, f, flip_rows=flip)
+    dst = np.full((h, w, 4), 7.0, np.float32)
+    p.set_image("Output", 0, dst, flip_rows=flip)
+    assert p.render(0, (0, 0, w, h)) == 0 and p.images_outstanding() == 0
+    g0 = ctx.rgba32f_to_srgb_gray8(frames[0] if not flip else frames[0][::-1])
+    g1 = ctx.rgba32f_to_srgb_gray8(frames[1] if not flip else frames[1][::-1])
+    assert np.array_equal(g0, gray[0] if not flip else gray[0][::-1])          # the staging conversion round-trips the bytes
+    ref = ctx.farneback(g0, g1, pkg.FbParams(levels=2, iterations=3))
+    got = dst if not flip else dst[::-1]
+    assert np.array_equal(got[..., 0], ref[..., 0]) and np.array_equal(got[..., 1], ref[..., 1])
+    assert not got[..., 2].any() and not got[..., 3].any()
+    p.close()
