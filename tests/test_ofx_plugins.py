@@ -320,3 +320,24 @@ def test_vectorgenerator_plugin_large_host_images(mh, pkg, ctx, oracle, synth, f
     assert np.array_equal(got[..., 0], ref[..., 0]) and np.array_equal(got[..., 1], ref[..., 1])
     assert not got[..., 2].any() and not got[..., 3].any()
     p.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flip", [False, True])
+def test_inpaint_plugin_large_host_images(mh, pkg, ctx, synth, flip):
+    """A 1500x1600 RGBA8 clip (9.6 MB) goes through the chunked staging path; sub-window render with an offset origin.
+    The render equals the C ABI composition called directly (split + dilate, inpaint, merge)."""
+    h, w = 1500, 1600
+    rgba, hole = _rgba_with_holes(synth, h, w, 5, 0.01)
+    p = mh.Plugin("inpaint")
+    assert p.create_instance() == 0
+    dst = np.zeros_like(rgba)
+    p.set_image("Source", 0, rgba, flip_rows=flip)
+    p.set_image("Output", 0, dst, flip_rows=flip)
+    assert p.render(0, (0, 0, w, h)) == 0 and p.images_outstanding() == 0
+    src = rgba if not flip else rgba[::-1]
+    rgb, mask = ctx.rgba8_to_rgb8_mask(np.ascontiguousarray(src), 1)
+    ref = ctx.inpaint(rgb, mask, 3, pkg.INPAINT_TELEA)
+    got = dst if not flip else dst[::-1]
+    assert np.array_equal(got[..., :3], ref) and (got[..., 3] == 255).all()
+    p.close()
