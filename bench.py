@@ -260,7 +260,7 @@ def run_ours(args):
     ms_one_lane = timed(step_resident, args.steps)
     ctx.timing(False)
     n_iter, iter_ms = ctx.kernel_time_ms(0)
-    ctx.farneback_set_lanes(2)
+    ctx.farneback_set_lanes(0)   # back to the default (by frame size: two pairs in flight at 4K)
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)

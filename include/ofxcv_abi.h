@@ -128,9 +128,10 @@ OFXCV_API int ofxcv_farneback_u8_keyed(ofxcv_ctx* ctx, ofxcv_stream stream, cons
  * renders of a clip (and the forward / backward flow of one render) share frame pyramids. */
 OFXCV_API int ofxcv_content_key_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* img, ptrdiff_t stride, int W,
                                    int H, uint64_t* key);
-/* pairs in flight inside ofxcv_farneback_sequence_u8 (default 2: pair t is solved on lane t&1, each lane with its own
- * stream and workspace, so that the latency-bound coarse scales of one pair overlap the bandwidth-bound fine scales
- * of the other; 1 = strictly one kernel at a time, what bench.py uses to time the dominant kernel on its own). */
+/* pairs in flight inside the clip entry points: pair t is solved on lane t % lanes, each lane with its own stream and
+ * workspace, so that the latency-bound coarse scales of one pair overlap the bandwidth-bound fine scales of another.
+ * 0 (default) = by frame size: 2 lanes from ~4 Mpx up (two 4K solves fill the GPU), 4 below; 1..4 fixes it; 1 =
+ * strictly one kernel at a time, what bench.py uses to time the dominant kernel on its own. */
 OFXCV_API void ofxcv_farneback_set_lanes(ofxcv_ctx* ctx, int lanes);
 OFXCV_API void ofxcv_farneback_cache_clear(ofxcv_ctx* ctx);
 /* pyramids built / cache hits since the context was created */

@@ -9,6 +9,8 @@
 
 #include "../../include/ofxcv_abi.h"
 
+constexpr int OFXCV_FB_MAX_LANES = 4;  // Farneback pairs in flight in the clip entry points
+
 struct ofxcv_buf {
     void* p = nullptr;
     size_t cap = 0;
@@ -24,8 +26,8 @@ struct ofxcv_fb_pyr {
     uint64_t tick = 0;   // LRU
     size_t off_q[16] = {0}, off_s[16] = {0};
     cudaEvent_t built = nullptr;  // recorded on the build stream after the pyramid is complete
-    cudaEvent_t used[2] = {nullptr, nullptr};  // recorded on a solve lane's stream after a solve that read it
-    bool used_pending[2] = {false, false};
+    cudaEvent_t used[OFXCV_FB_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};  // recorded on a solve lane's stream after a solve that read it
+    bool used_pending[OFXCV_FB_MAX_LANES] = {false, false, false, false};
 };
 
 struct ofxcv_timed_launch {
@@ -39,7 +41,7 @@ struct ofxcv_ctx {
     std::string last_error;
     uint64_t launches = 0;
     // named device workspaces, grown on demand, reused between calls
-    ofxcv_buf ws[56];
+    ofxcv_buf ws[72];
     // pinned host staging for the *_host entry points
     ofxcv_buf pin[13];  // 0-3 internal staging, 4-11 ofxcv_scratch_pinned, 12 Dual TV-L1 stop flags
     // per-family kernel timing (bench.py roofline numerator): events recorded on the launching stream
@@ -56,13 +58,13 @@ struct ofxcv_ctx {
         cudaEvent_t a, b;
     };
     std::vector<prof_rec> prof;
-    ofxcv_fb_pyr fb_pyr[4];
+    ofxcv_fb_pyr fb_pyr[8];  // >= lanes + 2: the pyramids of the pairs in flight + the one being built
     uint64_t fb_tick = 0;
     uint64_t fb_pyr_built = 0, fb_pyr_hits = 0;
-    int fb_lanes = 2;  // pairs in flight in ofxcv_farneback_sequence_u8 (ofxcv_farneback_set_lanes)
+    int fb_lanes = 0;  // pairs in flight in ofxcv_farneback_sequence_u8: 0 = by frame size (ofxcv_farneback_set_lanes)
     // copy streams + events of the *_sequence_host entry points (created on first use)
-    cudaStream_t stream_up = nullptr, stream_down = nullptr, stream_lane[2] = {nullptr, nullptr};
-    cudaEvent_t lane_done[2] = {nullptr, nullptr}, lane_start = nullptr;
+    cudaStream_t stream_up = nullptr, stream_down = nullptr, stream_lane[OFXCV_FB_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t lane_done[OFXCV_FB_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}, lane_start = nullptr;
     cudaEvent_t seq_ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     ofxcv_ctx* sub[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // workers of ofxcv_inpaint_sequence_u8 (owned)
     int ip_fill_blocks_per_sm = 8;  // persistent CTAs of the inpaint fill kernel per SM (ofxcv_inpaint_set_fill_blocks)
@@ -186,7 +188,21 @@ enum {
     WS_FB1_FLOWA,
     WS_FB1_FLOWB,
     WS_FB1_TOT,
+    WS_FB2_MAQ,  // lanes 2 and 3: same seven slots in the same order
+    WS_FB2_MAS,
+    WS_FB2_MBQ,
+    WS_FB2_MBS,
+    WS_FB2_FLOWA,
+    WS_FB2_FLOWB,
+    WS_FB2_TOT,
+    WS_FB3_MAQ,
+    WS_FB3_MAS,
+    WS_FB3_MBQ,
+    WS_FB3_MBS,
+    WS_FB3_FLOWA,
+    WS_FB3_FLOWB,
+    WS_FB3_TOT,
     WS_TV_ARENA,  // Dual TV-L1: pyramids + J/A/P/U planes + control block, one allocation
     WS_COUNT
 };
-static_assert(WS_COUNT + 8 <= 56, "workspace slots (the last 8 are ofxcv_scratch_device)");
+static_assert(WS_COUNT + 8 <= 72, "workspace slots (the last 8 are ofxcv_scratch_device)");

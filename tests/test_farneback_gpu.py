@@ -106,7 +106,8 @@ def test_keyed_forward_backward_shares_pyramids(ctx, pkg, synth):
     assert np.array_equal(out_b.download((h, w, 2), np.float32), ref_b)
     # a different size under the same key must not hit
     small = synth.gray(synth.texture(64, 80, seed=13))
-    ctx.farneback_keyed_dev(ctx.to_device(small).ptr, ctx.to_device(small).ptr, 80, 64, ctx.alloc(80 * 64 * 8).ptr, 1001, 1002, p)
+    s0, s1, sf = ctx.to_device(small), ctx.to_device(small), ctx.alloc(80 * 64 * 8)   # alive until the synchronize below
+    ctx.farneback_keyed_dev(s0.ptr, s1.ptr, 80, 64, sf.ptr, 1001, 1002, p)
     ctx.synchronize()
     b2, h2 = ctx.farneback_cache_stats()
     assert b2 - b1 == 2 and h2 == h1
@@ -117,8 +118,9 @@ def test_content_key(ctx, synth):
     b = a.copy()
     b[10, 10] ^= 1
     c = np.ascontiguousarray(a[:, ::-1])          # same histogram, different positions
-    ka, kb, kc = (ctx.content_key(ctx.to_device(x).ptr, 80, 64) for x in (a, b, c))
-    assert ka == ctx.content_key(ctx.to_device(a.copy()).ptr, 80, 64)
+    bufs = [ctx.to_device(x) for x in (a, b, c, a.copy())]    # keep the device buffers alive while their keys are taken
+    ka, kb, kc, ka2 = (ctx.content_key(d.ptr, 80, 64) for d in bufs)
+    assert ka == ka2
     assert len({ka, kb, kc}) == 3 and 0 not in (ka, kb, kc)
 
 
