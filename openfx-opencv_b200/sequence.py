@@ -61,8 +61,10 @@ def run_sharded(n_units, process_unit, world=None, rank=None):
     return [merged[i] for i in range(n_units)]
 
 
-def flow_clip(ctx, load_frame, n_frames, params=None, world=None, rank=None, keep=True):
+def flow_clip(ctx, load_frame, n_frames, params=None, world=None, rank=None, keep=True, method="farneback"):
     """Forward flow t -> t+1 of a whole clip, frame-sharded over the ranks of the default process group.
+    method = "farneback" (one clip call, pyramids shared between pairs) or "tvl1" (the plugin's second method, pair by
+    pair: it has no per-frame state to share).
 
     load_frame(t) -> HxW uint8 (host) is called only for the frames this rank needs (its contiguous block of outputs
     plus the one-frame halo).  The rank's block goes through ONE clip call of the C ABI (ofxcv_farneback_sequence_u8_host:
@@ -79,7 +81,12 @@ def flow_clip(ctx, load_frame, n_frames, params=None, world=None, rank=None, kee
         frames = [np.ascontiguousarray(load_frame(t), np.uint8) for t in frames_needed(first, count, n_frames)]
         if inited:
             dist.barrier()
-        flows = ctx.farneback_sequence(frames, params)
+        if method == "farneback":
+            flows = ctx.farneback_sequence(frames, params)
+        elif method == "tvl1":
+            flows = [ctx.tvl1(a, b, params)[0] for a, b in zip(frames[:-1], frames[1:])]
+        else:
+            raise ValueError("method must be 'farneback' or 'tvl1'")
     elif inited:
         dist.barrier()
     mine = [(first + i, checksum64(f)) for i, f in enumerate(flows)]

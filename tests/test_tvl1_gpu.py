@@ -88,3 +88,17 @@ def test_tvl1_1080p_recovers_translation(pkg, ctx, synth):
     assert it > 0
     flow2, it2 = ctx.tvl1(prev, nxt, par)
     assert it2 == it and np.array_equal(flow, flow2)
+
+
+def test_tvl1_clip_driver_single_rank(pkg, ctx, synth):
+    """sequence.flow_clip with method="tvl1": every pair of the clip equals the pair call."""
+    import importlib
+    seq = importlib.import_module("openfx-opencv_b200.sequence")
+    base = synth.gray(synth.texture(48, 64, seed=17))
+    frames = [synth.shift_bilinear(base, 1.0 * t, -0.5 * t) for t in range(4)]
+    par = pkg.Tvl1Params(nscales=3, warps=2, iterations=4, outer_iterations=2)
+    first, flows, sums = seq.flow_clip(ctx, lambda t: frames[t], len(frames), par, method="tvl1")
+    assert first == 0 and len(flows) == 3
+    for t in range(3):
+        ref, _ = ctx.tvl1(frames[t], frames[t + 1], par)
+        assert np.array_equal(flows[t], ref) and sums[t] == seq.checksum64(ref)
