@@ -192,6 +192,127 @@ __global__ void __launch_bounds__(256) ip_pass_c(uint8_t* __restrict__ st, const
     }
 }
 
+// ---- the same three passes over 16 / 4 pixels per thread ----------------------------------------------------------
+// The state map is one byte per pixel and most of it is OUT / POPPED / INSIDE-far-from-the-front in every batch: a
+// thread reads 16 (passes A, B) or 4 (pass C) states with one load, tests them with byte-wise SIMD compares and only
+// looks at T / neighbours for the few bytes that matter.  The map is padded to a multiple of 16 with OUT bytes.
+__device__ __forceinline__ bool ip_any_byte(uint32_t w, uint32_t v) { return __vcmpeq4(w, v * 0x01010101u) != 0; }
+
+__global__ void __launch_bounds__(256) ip_pass_a16(uint4* __restrict__ st16, const float* __restrict__ t, unsigned* __restrict__ tau_bits, int n16)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned local = 0xffffffffu;
+    if (i < n16) {
+        const uint4 w4 = st16[i];
+        uint32_t v[4] = {w4.x, w4.y, w4.z, w4.w};
+        bool changed = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t w = v[q];
+            if (!(ip_any_byte(w, ST_HEAP) || ip_any_byte(w, ST_SELECTED) || ip_any_byte(w, ST_NEW))) continue;
+            uint32_t o = w;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                uint32_t sb = (w >> (8 * b)) & 0xffu;
+                if (sb == ST_SELECTED) sb = ST_POPPED;
+                else if (sb == ST_NEW) sb = ST_HEAP;
+                o = (o & ~(0xffu << (8 * b))) | (sb << (8 * b));
+                if (sb == ST_HEAP) local = min(local, __float_as_uint(t[(size_t)i * 16 + q * 4 + b]));
+            }
+            changed |= o != w;
+            v[q] = o;
+        }
+        if (changed) st16[i] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+    __shared__ unsigned wmin[8];
+    local = __reduce_min_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        local = __reduce_min_sync(0xffffffffu, threadIdx.x < 8 ? wmin[threadIdx.x] : 0xffffffffu);
+        if (threadIdx.x == 0 && local != 0xffffffffu) atomicMin(tau_bits, local);
+    }
+}
+
+__global__ void __launch_bounds__(256) ip_pass_b16(uint4* __restrict__ st16, const float* __restrict__ t, const unsigned* __restrict__ tau_bits, int n16)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    const uint4 w4 = st16[i];
+    uint32_t v[4] = {w4.x, w4.y, w4.z, w4.w};
+    bool changed = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t w = v[q];
+        if (!ip_any_byte(w, ST_HEAP)) continue;
+        const float lim = __uint_as_float(*tau_bits) + 0.7f;
+        uint32_t o = w;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (((w >> (8 * b)) & 0xffu) == ST_HEAP && t[(size_t)i * 16 + q * 4 + b] < lim)
+                o = (o & ~(0xffu << (8 * b))) | ((uint32_t)ST_SELECTED << (8 * b));
+        changed |= o != w;
+        v[q] = o;
+    }
+    if (changed) st16[i] = make_uint4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void __launch_bounds__(256) ip_pass_c4(const uint8_t* __restrict__ st, const float* __restrict__ t, const uint32_t* __restrict__ cnt,
+                                                  unsigned long long* __restrict__ keys, uint32_t* __restrict__ ids,
+                                                  unsigned* __restrict__ n_new, int n4, IpGeom g)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long best[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+    int nhit = 0;
+    if (i < n4) {
+        const uint32_t w = reinterpret_cast<const uint32_t*>(st)[i];
+        if (ip_any_byte(w, ST_INSIDE)) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                if (((w >> (8 * b)) & 0xffu) != ST_INSIDE) continue;
+                const int id = i * 4 + b;  // INSIDE pixels are interior: all four neighbours exist
+                const int nb[4] = {id - g.ec, id - 1, id + g.ec, id + 1};
+                const unsigned slot[4] = {2u, 3u, 0u, 1u};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int p = nb[q];
+                    if (st[p] == ST_SELECTED) {
+                        const unsigned long long k = ((unsigned long long)__float_as_uint(t[p]) << 32) | ((unsigned long long)cnt[p] << 2) | slot[q];
+                        best[b] = k < best[b] ? k : best[b];
+                    }
+                }
+                nhit += best[b] != ~0ull;
+            }
+        }
+    }
+    // append: exclusive scan of the per-thread counts inside the warp, warp totals in shared memory, one global atomic
+    __shared__ unsigned wcount[8], base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned incl = nhit;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) wcount[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const unsigned c = wcount[k]; wcount[k] = tot; tot += c; }
+        base = tot ? atomicAdd(n_new, tot) : 0u;
+    }
+    __syncthreads();
+    unsigned pos = base + wcount[wid] + incl - nhit;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        if (best[b] != ~0ull) {
+            keys[pos] = best[b];
+            ids[pos] = (uint32_t)(i * 4 + b);
+            pos++;
+        }
+}
+
 // after the sort: hand out push counters in fill order; the hole pass also records the fill order itself
 __global__ void __launch_bounds__(256) ip_assign(const uint32_t* __restrict__ ids_sorted, unsigned n, uint32_t base,
                                                  uint8_t* __restrict__ st, uint32_t* __restrict__ cnt, uint32_t* __restrict__ order,
@@ -957,7 +1078,8 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
     IpGeom g;
     g.W = W; g.H = H; g.er = H + 2; g.ec = W + 2; g.np = g.er * g.ec;
     const size_t np = (size_t)g.np;
-    uint8_t* bytes = (uint8_t*)ofxcv_ws(ctx, WS_INP_A, np * 5);
+    const size_t npa = (np + 15) & ~(size_t)15;  // the byte maps start on 16-byte boundaries (16-pixel passes over `st`)
+    uint8_t* bytes = (uint8_t*)ofxcv_ws(ctx, WS_INP_A, npa * 5);
     uint16_t* rnd = (uint16_t*)ofxcv_ws(ctx, WS_INP_B, np * 2);
     float* t = (float*)ofxcv_ws(ctx, WS_INP_C, np * 4);
     uint32_t* u32s = (uint32_t*)ofxcv_ws(ctx, WS_INP_D, np * 4 * 4);
@@ -965,7 +1087,7 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
     IpCounters* ctr = (IpCounters*)ofxcv_ws(ctx, WS_INP_F, sizeof(IpCounters));
     IpCounters* hctr = (IpCounters*)ofxcv_pin(ctx, 2, sizeof(IpCounters));
     if (!bytes || !rnd || !t || !u32s || !keys || !ctr || !hctr) return OFXCV_ERR_MEMORY;
-    uint8_t *hole = bytes, *outreg = bytes + np, *tmp = bytes + 2 * np, *st = bytes + 3 * np, *done = bytes + 4 * np;
+    uint8_t *hole = bytes, *outreg = bytes + npa, *tmp = bytes + 2 * npa, *st = bytes + 3 * npa, *done = bytes + 4 * npa;
     uint32_t *cnt = u32s, *order = u32s + np, *ids = u32s + 2 * np, *ids_sorted = u32s + 3 * np;
     unsigned long long* keys_sorted = keys + np;
     size_t sort_tmp_bytes = 0;
@@ -1003,6 +1125,8 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
         OFXCV_LAUNCH_CHECK(ctx);
     }
     uint32_t nfilled = 0;
+    static const bool wide_passes = !getenv("OFXCV_IP_PASSES_V1");
+    if (npa > np) OFXCV_CUDA(ctx, cudaMemsetAsync(st + np, ST_OUT, npa - np, s));  // padding of the state map: never in the heap
     for (int pass = (method == OFXCV_INPAINT_TELEA ? 1 : 0); pass >= 0; pass--) {
         const int outer = pass;  // Telea: pass 1 = outside band (negated afterwards), pass 0 = the hole itself
         ip_setup_pass<<<nblk, 256, 0, s>>>(hole, outreg, st, t, cnt, rnd, outer, g);
@@ -1012,12 +1136,22 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
             ofxcv_prof_scope ps(ctx, s, "ip_march_batch", pass);
             OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->tau_bits, 0xff, sizeof(unsigned), s));
             OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->n_new, 0, sizeof(unsigned), s));
-            ip_pass_a<<<nblk, 256, 0, s>>>(st, t, &ctr->tau_bits, g);
-            OFXCV_LAUNCH_CHECK(ctx);
-            ip_pass_b<<<nblk, 256, 0, s>>>(st, t, &ctr->tau_bits, g);
-            OFXCV_LAUNCH_CHECK(ctx);
-            ip_pass_c<<<nblk, 256, 0, s>>>(st, t, cnt, keys, ids, &ctr->n_new, g);
-            OFXCV_LAUNCH_CHECK(ctx);
+            if (wide_passes) {
+                const int n16 = (int)(npa / 16), n4 = (int)(npa / 4);
+                ip_pass_a16<<<ofxcv_div_up(n16, 256), 256, 0, s>>>((uint4*)st, t, &ctr->tau_bits, n16);
+                OFXCV_LAUNCH_CHECK(ctx);
+                ip_pass_b16<<<ofxcv_div_up(n16, 256), 256, 0, s>>>((uint4*)st, t, &ctr->tau_bits, n16);
+                OFXCV_LAUNCH_CHECK(ctx);
+                ip_pass_c4<<<ofxcv_div_up(n4, 256), 256, 0, s>>>(st, t, cnt, keys, ids, &ctr->n_new, n4, g);
+                OFXCV_LAUNCH_CHECK(ctx);
+            } else {
+                ip_pass_a<<<nblk, 256, 0, s>>>(st, t, &ctr->tau_bits, g);
+                OFXCV_LAUNCH_CHECK(ctx);
+                ip_pass_b<<<nblk, 256, 0, s>>>(st, t, &ctr->tau_bits, g);
+                OFXCV_LAUNCH_CHECK(ctx);
+                ip_pass_c<<<nblk, 256, 0, s>>>(st, t, cnt, keys, ids, &ctr->n_new, g);
+                OFXCV_LAUNCH_CHECK(ctx);
+            }
             OFXCV_CUDA(ctx, cudaMemcpyAsync(hctr, ctr, sizeof(IpCounters), cudaMemcpyDeviceToHost, s));
             OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
             if (hctr->tau_bits == 0xffffffffu) break;  // heap empty
