@@ -386,6 +386,72 @@ __global__ void __launch_bounds__(256) ip_round(const uint32_t* __restrict__ ids
     rnd[id] = (uint16_t)round;
 }
 
+// The same relaxation in ONE launch per batch.  A reached pixel depends only on 4-neighbours reached EARLIER in the batch,
+// i.e. on entries with a smaller index in the sorted list, so the chains can be followed inside the kernel: blocks take
+// their index from a ticket (a block that holds a ticket is running and every lower ticket is running or finished, so
+// waiting on lower indices cannot deadlock), a warp polls the stamps of the neighbours its lanes still miss and every
+// lane computes as soon as its own are there (no lane ever blocks another lane of its warp).  T is published with a
+// fence before the stamp; readers take the stamp with an acquire load.  Each T is computed exactly once from final
+// neighbour values, as in the round-by-round version.
+__global__ void __launch_bounds__(256) ip_round_chain(const uint32_t* __restrict__ ids_sorted, unsigned n, const uint8_t* __restrict__ st,
+                                                      float* t, const uint32_t* __restrict__ cnt, uint16_t* rnd, unsigned* __restrict__ ticket,
+                                                      IpGeom g)
+{
+    __shared__ unsigned bid;
+    if (threadIdx.x == 0) bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned i = bid * blockDim.x + threadIdx.x;
+    bool active = i < n;
+    uint32_t id = 0;
+    int nb[4] = {0, 0, 0, 0};
+    bool known[4] = {false, false, false, false}, wait[4] = {false, false, false, false};
+    float tv[4] = {T_FAR, T_FAR, T_FAR, T_FAR};
+    if (active) {
+        id = ids_sorted[i];
+        const uint32_t mycnt = cnt[id];
+        nb[0] = (int)id - g.ec; nb[1] = (int)id + g.ec; nb[2] = (int)id - 1; nb[3] = (int)id + 1;  // up, down, left, right
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint8_t s = st[nb[q]];
+            if (s == ST_INSIDE) known[q] = false;
+            else if (s == ST_NEW) {
+                known[q] = cnt[nb[q]] < mycnt;
+                wait[q] = known[q];      // its T is being computed in this very launch
+            } else known[q] = true;
+            if (known[q] && !wait[q]) tv[q] = t[nb[q]];
+        }
+    }
+    bool done = !active;
+    while (!__all_sync(0xffffffffu, done)) {
+        if (!done) {
+            bool ready = true;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (wait[q]) {
+                    if (*((volatile uint16_t*)rnd + nb[q]) != 0) {  // relaxed poll, then ONE acquire load (see ip_fill_staged)
+                        unsigned stamp;
+                        asm volatile("ld.acquire.gpu.global.u16 %0, [%1];" : "=r"(stamp) : "l"(rnd + nb[q]) : "memory");
+                        tv[q] = *((volatile float*)t + nb[q]);
+                        wait[q] = false;
+                    } else ready = false;
+                }
+            if (ready) {
+                // min4(solve(i-1,j,i,j-1), solve(i+1,j,i,j-1), solve(i-1,j,i,j+1), solve(i+1,j,i,j+1))
+                float a = fmm_solve(known[0], known[2], tv[0], tv[2]);
+                float b = fmm_solve(known[1], known[2], tv[1], tv[2]);
+                float c = fmm_solve(known[0], known[3], tv[0], tv[3]);
+                float d = fmm_solve(known[1], known[3], tv[1], tv[3]);
+                a = a < b ? a : b;
+                c = c < d ? c : d;
+                *((volatile float*)t + id) = a < c ? a : c;
+                __threadfence();
+                *((volatile uint16_t*)rnd + id) = 1;
+                done = true;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) ip_negate(const uint8_t* __restrict__ st, const uint8_t* __restrict__ outreg, float* __restrict__ t, IpGeom g)
 {
     int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1126,6 +1192,7 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
     }
     uint32_t nfilled = 0;
     static const bool wide_passes = !getenv("OFXCV_IP_PASSES_V1");
+    static const bool chain_rounds = !getenv("OFXCV_IP_ROUNDS_V1");
     if (npa > np) OFXCV_CUDA(ctx, cudaMemsetAsync(st + np, ST_OUT, npa - np, s));  // padding of the state map: never in the heap
     for (int pass = (method == OFXCV_INPAINT_TELEA ? 1 : 0); pass >= 0; pass--) {
         const int outer = pass;  // Telea: pass 1 = outside band (negated afterwards), pass 0 = the hole itself
@@ -1165,20 +1232,26 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
             OFXCV_LAUNCH_CHECK(ctx);
             next_cnt += n_new;
             if (!outer) nfilled += n_new;
-            // relaxation rounds until every reached pixel has its T
+            // T of the reached pixels: dependency chains followed inside one launch (round by round with OFXCV_IP_ROUNDS_V1)
             unsigned round = 1;
-            for (;;) {
-                const int burst = round == 1 ? 4 : 16;
-                for (int b = 0; b < burst; b++, round++) {
-                    if (round >= 65535) return OFXCV_ERR_UNSUPPORTED;
-                    OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->pending, 0, sizeof(unsigned), s));
-                    ip_round<<<nb2, 256, 0, s>>>(ids_sorted, n_new, st, t, cnt, rnd, round, &ctr->pending, g);
-                    OFXCV_LAUNCH_CHECK(ctx);
+            if (chain_rounds) {
+                OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->ticket, 0, sizeof(unsigned), s));
+                ip_round_chain<<<nb2, 256, 0, s>>>(ids_sorted, n_new, st, t, cnt, rnd, &ctr->ticket, g);
+                OFXCV_LAUNCH_CHECK(ctx);
+                round = 2;
+            } else
+                for (;;) {
+                    const int burst = round == 1 ? 4 : 16;
+                    for (int b = 0; b < burst; b++, round++) {
+                        if (round >= 65535) return OFXCV_ERR_UNSUPPORTED;
+                        OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->pending, 0, sizeof(unsigned), s));
+                        ip_round<<<nb2, 256, 0, s>>>(ids_sorted, n_new, st, t, cnt, rnd, round, &ctr->pending, g);
+                        OFXCV_LAUNCH_CHECK(ctx);
+                    }
+                    OFXCV_CUDA(ctx, cudaMemcpyAsync(hctr, ctr, sizeof(IpCounters), cudaMemcpyDeviceToHost, s));
+                    OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+                    if (hctr->pending == 0) break;
                 }
-                OFXCV_CUDA(ctx, cudaMemcpyAsync(hctr, ctr, sizeof(IpCounters), cudaMemcpyDeviceToHost, s));
-                OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
-                if (hctr->pending == 0) break;
-            }
             rounds_total += round - 1;
         }
         if (outer) {
