@@ -203,3 +203,12 @@ def test_farneback_c5_8k_levels5_properties(ctx, pkg, synth):
     c = a[400:-400, 400:-400]
     epe = np.hypot(c[..., 0] - 2.5, c[..., 1] + 1.5)
     assert epe.mean() < 0.5 and np.median(epe) < 0.3, (epe.mean(), np.median(epe))
+
+
+def test_farneback_720p_polyn7_levels4(ctx, pkg, oracle, synth):
+    """The other PolyExp instantiation (N = 7, sigma 1.5) on a 5-scale pyramid."""
+    prev, nxt = synth.flow_pair(720, 1280, seed=11, dx=3.25, dy=-2.5)
+    par = pkg.FbParams(levels=4, iterations=5, poly_n=7, poly_sigma=1.5)
+    got = ctx.farneback(prev, nxt, par)
+    ref = oracle.farneback(prev, nxt, levels=4, iters=5, poly_n=7, poly_sigma=1.5)
+    assert np.array_equal(got, ref)

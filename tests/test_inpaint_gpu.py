@@ -148,3 +148,13 @@ def test_inpaint_c4_4k_ns_10pct(ctx, oracle, synth):
     ref = oracle.inpaint(img, mask, 3, NS)
     assert int((got != ref).sum()) == 0
     assert np.array_equal(got[mask == 0], img[mask == 0])
+
+
+def test_inpaint_gray_1080p_telea_radius5(ctx, oracle, synth):
+    """One channel, a larger radius (81 -> 121 taps), blobs + iid holes together."""
+    h, w = 1080, 1920
+    img = synth.gray(synth.texture(h, w, 77))
+    mask = np.maximum(synth.iid_mask(h, w, 78, 0.03), synth.blob_mask(h, w, 79, 40, 12))
+    got = ctx.inpaint(img, mask, 5, TELEA)
+    ref = oracle.inpaint(img, mask, 5, TELEA)
+    assert int((got != ref).sum()) == 0

@@ -61,3 +61,12 @@ def test_watershed_clip_equals_frame_by_frame(pkg, ctx, oracle, synth):
     for (img, mk), lab, cs in zip(frames, labs, sums):
         ref, _ = oracle.watershed(img, mk)
         assert np.array_equal(lab, ref) and cs == seq.checksum64(ref)
+
+
+def test_watershed_1080p_1000_seeds(ctx, oracle, synth):
+    h, w = 1080, 1920
+    img = synth.texture(h, w, 91)
+    mk = synth.seed_markers(h, w, 1000, 92)
+    got = ctx.watershed(img, mk)
+    ref, pops = oracle.watershed(img, mk)
+    assert np.array_equal(got, ref) and ctx.watershed_stats()["pops"] == pops
