@@ -693,7 +693,7 @@ template <int METHOD, int CN, bool READYQ>
 __global__ void __launch_bounds__(IP_WARPS * 32, READYQ ? 2 : 4)  // in-order tickets: the resident-warp count is the window over the chains
 ip_fill_staged(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __restrict__ fidx, const float* __restrict__ t,
                uint8_t* out, ptrdiff_t ostride, uint8_t* done, int32_t* dep, int32_t* rq, unsigned* __restrict__ ticket,
-               unsigned* __restrict__ rtail, int range, IpGeom g)
+               unsigned* __restrict__ rtail, uint32_t* pub, int range, IpGeom g)
 {
     constexpr int NACC = METHOD == OFXCV_INPAINT_TELEA ? 4 * CN : 2 * CN;
     extern __shared__ __align__(16) unsigned char ip2_smem[];
@@ -776,17 +776,43 @@ ip_fill_staged(const uint32_t* __restrict__ order, unsigned nfill, const int32_t
             s_px[b] = (fi < (int)tk ? 1u : 0u) << 24;
         };
         // (b) colours (+T) of the box in one round
-        auto stage_b = [&](int k, int l, uint32_t& px, float& tv) {
+        auto stage_b = [&](int k, int l, uint32_t& px, float& tv, bool colour = true) {
             px = 0;
             tv = 0.f;
-            if (k >= 1 && l >= 1 && k <= g.H && l <= g.W) {
+            if (colour && k >= 1 && l >= 1 && k <= g.H && l <= g.W) {
                 const uint8_t* o = out + (size_t)(k - 1) * ostride + (size_t)(l - 1) * CN;
 #pragma unroll
                 for (int c = 0; c < CN; c++) px |= (uint32_t)ld_u8_cg(o + c) << (8 * c);
             }
             if (METHOD == OFXCV_INPAINT_TELEA && k >= 0 && l >= 0 && k < er && l < ec) tv = __ldg(t + k * ec + l);
         };
-        if (tabulated) {
+        if (tabulated && !READYQ) {
+            // In-order tickets, small boxes: an earlier-filled hole pixel publishes ONE word, its colour with a "done" bit
+            // (pub[fill index]).  Flag and data travel together, so the dependent warp needs neither an acquire nor a second
+            // round trip for the colour, and the finishing warp no release fence; everything that does not depend on a
+            // pending pixel is loaded BEFORE the wait, so the chain step is: poll -> stage -> taps -> publish.
+            int fi[IP2_NPOS], nn[IP2_NPOS];
+            uint32_t px[IP2_NPOS];
+            float tv[IP2_NPOS];
+#pragma unroll
+            for (int q = 0; q < IP2_NPOS; q++)
+                if (pk[q] >= 0) stage_a(q * 32 + lane, k0 + pk[q], l0 + pl[q], fi[q], nn[q]);
+#pragma unroll
+            for (int q = 0; q < IP2_NPOS; q++)
+                if (pk[q] >= 0) stage_b(k0 + pk[q], l0 + pl[q], px[q], tv[q], !(fi[q] >= 0 && fi[q] < (int)tk));
+#pragma unroll
+            for (int q = 0; q < IP2_NPOS; q++)
+                if (pk[q] >= 0) {
+                    if (fi[q] >= 0 && fi[q] < (int)tk) {
+                        volatile uint32_t* w = pub + fi[q];
+                        uint32_t v;
+                        while (((v = *w) & 0x80000000u) == 0) { }
+                        px[q] = v & 0x00ffffffu;
+                    }
+                    s_px[q * 32 + lane] = ((fi[q] < (int)tk ? 1u : 0u) << 24) | px[q];
+                    s_t[q * 32 + lane] = tv[q];
+                }
+        } else if (tabulated) {
             int fi[IP2_NPOS], nn[IP2_NPOS];
 #pragma unroll
             for (int q = 0; q < IP2_NPOS; q++)
@@ -1050,13 +1076,19 @@ ip_fill_staged(const uint32_t* __restrict__ order, unsigned nfill, const int32_t
             int iv = __double2int_rn((double)Ia / s);
             result = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
         }
+        if (!READYQ && tabulated) {  // colour + done bit in one word: what the dependents poll
+            uint32_t word = 0x80000000u;
+#pragma unroll
+            for (int c = 0; c < CN; c++) word |= (uint32_t)__shfl_sync(0xffffffffu, (unsigned)result, c) << (8 * c);
+            if (lane == 0) *((volatile uint32_t*)pub + tk) = word;
+        }
         if (lane < CN) {
             volatile uint8_t* o = out + (size_t)(i - 1) * ostride + (size_t)(j - 1) * CN + lane;
             *o = result;
         }
         __syncwarp();
         if (!READYQ) {
-            if (lane == 0) {  // release: the colour bytes stored by lanes 0..CN-1 (ordered by the barrier above) before the flag
+            if (!tabulated && lane == 0) {  // release: the colour bytes stored by lanes 0..CN-1 (ordered by the barrier above) before the flag
                 asm volatile("st.release.gpu.global.u8 [%0], %1;" ::"l"(done + id), "r"(1u) : "memory");
             }
         } else {
@@ -1281,6 +1313,8 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
         // (cheaper per chain step; what an iid mask wants).  OFXCV_IP_READYQ=0/1 forces one.
         int32_t* dep = (int32_t*)keys;  // the sort buffers are free once the march is over
         int32_t* rq = dep + np;
+        uint32_t* pub = (uint32_t*)(rq + np);  // colour + done word per fill index (in-order scheduler)
+        OFXCV_CUDA(ctx, cudaMemsetAsync(pub, 0, (size_t)nfilled * 4, s));
         bool ready_queue = false;
         if (v2) {
             OFXCV_CUDA(ctx, cudaMemsetAsync(rq, 0xff, (size_t)nfilled * 4, s));
@@ -1307,11 +1341,11 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
             if (ready_queue)                                                                                                       \
                 ip_fill_staged<M, C, true><<<blocks, IP_WARPS * 32, fill_smem, s>>>(order, nfilled, fidx, t, out, out_stride,     \
                                                                                     done, dep, rq, &ctr->ticket, &ctr->pending,   \
-                                                                                    range, g);                                     \
+                                                                                    pub, range, g);                                \
             else                                                                                                                   \
                 ip_fill_staged<M, C, false><<<blocks, IP_WARPS * 32, fill_smem, s>>>(order, nfilled, fidx, t, out, out_stride,    \
                                                                                      done, dep, rq, &ctr->ticket, &ctr->pending,  \
-                                                                                     range, g);                                    \
+                                                                                     pub, range, g);                               \
         } else {                                                                                                                   \
             ip_fill<M, C><<<blocks, IP_WARPS * 32, 0, s>>>(order, nfilled, (uint32_t)g.np, hole, cnt, t, out, out_stride, done,    \
                                                            &ctr->ticket, range, g);                                                \
