@@ -800,14 +800,21 @@ ip_fill_staged(const uint32_t* __restrict__ order, unsigned nfill, const int32_t
 #pragma unroll
             for (int q = 0; q < IP2_NPOS; q++)
                 if (pk[q] >= 0) stage_b(k0 + pk[q], l0 + pl[q], px[q], tv[q], !(fi[q] >= 0 && fi[q] < (int)tk));
+            // first look at all of this lane's dependencies at once (one round trip when they are already there, the
+            // usual case), then spin only on the ones still missing
+            uint32_t pv[IP2_NPOS];
+#pragma unroll
+            for (int q = 0; q < IP2_NPOS; q++) {
+                pv[q] = 0x80000000u;
+                if (pk[q] >= 0 && fi[q] >= 0 && fi[q] < (int)tk) pv[q] = *((volatile uint32_t*)pub + fi[q]);
+            }
 #pragma unroll
             for (int q = 0; q < IP2_NPOS; q++)
                 if (pk[q] >= 0) {
                     if (fi[q] >= 0 && fi[q] < (int)tk) {
                         volatile uint32_t* w = pub + fi[q];
-                        uint32_t v;
-                        while (((v = *w) & 0x80000000u) == 0) { }
-                        px[q] = v & 0x00ffffffu;
+                        while ((pv[q] & 0x80000000u) == 0) pv[q] = *w;
+                        px[q] = pv[q] & 0x00ffffffu;
                     }
                     s_px[q * 32 + lane] = ((fi[q] < (int)tk ? 1u : 0u) << 24) | px[q];
                     s_t[q * 32 + lane] = tv[q];
