@@ -15,8 +15,10 @@ sharded one block per GPU with no data-path collective (weak scaling: per-GPU wo
            algorithmic bytes per launch (88 B per pixel: SURVEY.md 8d) / its average CUDA-event duration inside the
            timed region, against the measured HBM copy peak in MEASURED_PEAKS.json (fallback 6650 GB/s); `traffic` =
            dram bytes read+written per launch from the committed `ncu --set full` capture (profiles/*.json);
-  plugins = the other two plugin bodies at 4K on the same GPU (rank 0, N=1 only): NS / Telea inpaint 10 % mask and
-           watershed 256 seeds, frames resident in HBM, with their CPU reference (cv2) timed beside them;
+  plugins = the other plugin bodies at 4K on the same GPU (rank 0, N=1 only), frames resident in HBM: NS / Telea inpaint
+           of a 10 % mask (one frame, and a 32-frame clip with 8 frames in flight through ofxcv_inpaint_sequence_u8),
+           watershed with 256 seeds (1 and 512 frames in flight), Dual TV-L1 with the plugin defaults (+ its iteration
+           kernel alone); the CPU reference (cv2; for TV-L1 the CPU port on a 1/36-area sample) timed beside them;
   cpu_baseline = the reference arm run once on this box's host cores on a bounded sample (rank 0, N=1 only).
 """
 import argparse
