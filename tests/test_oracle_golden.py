@@ -132,3 +132,19 @@ def test_tvl1_oracle_recovers_a_translation(oracle, synth):
     assert 0 < iters < 5 * 5 * 10 * 15
     flow2, iters2 = oracle.tvl1(base, nxt)
     assert iters2 == iters and np.array_equal(flow, flow2)
+
+
+def test_tvl1_oracle_properties(oracle, synth):
+    """More sanity of the unpinned restatement: identical frames give exactly zero flow and stop at once; the backward
+    flow of a translated pair is close to the negated forward flow; a larger epsilon never runs more iterations."""
+    base = synth.gray(synth.texture(96, 128, seed=9))
+    flow, iters = oracle.tvl1(base, base)
+    assert not flow.any() and iters == 5 * 5          # one inner iteration per warping, then the early exit
+    nxt = synth.shift_bilinear(base, 1.5, 0.75)
+    fwd, it_f = oracle.tvl1(base, nxt)
+    bwd, _ = oracle.tvl1(nxt, base)
+    inner = (slice(12, -12), slice(12, -12))
+    assert np.abs(fwd[inner] + bwd[inner]).mean() < 0.1
+    assert abs(np.median(fwd[inner][..., 0]) - 1.5) < 0.05 and abs(np.median(fwd[inner][..., 1]) - 0.75) < 0.05
+    _, it_loose = oracle.tvl1(base, nxt, epsilon=0.05)
+    assert it_loose <= it_f
