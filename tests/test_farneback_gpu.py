@@ -168,6 +168,19 @@ def test_farneback_4k_properties(ctx, pkg, synth):
     assert np.array_equal(seq[0], a) and np.array_equal(seq[1], ctx.farneback(f[1], f[2]))
 
 
+def test_farneback_4k_vs_oracle(ctx, pkg, oracle, synth):
+    """The bench's headline workload itself (3840x2160, default plugin parameters, the bench's frames: Texture(seed 2000)
+    and its (2.5, -1.5) px translate) against the CPU oracle (about 8 s), SURVEY.md 8c tolerances."""
+    h, w = 2160, 3840
+    base = synth.gray(synth.texture(h, w, seed=2000))
+    nxt = synth.shift_bilinear(base, 2.5, -1.5)
+    got = ctx.farneback(base, nxt)
+    ref = oracle.farneback(base, nxt)
+    mean, f2, f0, same = _stats(got, ref)
+    print("farneback 4K: mean %.3g frac>1e-2 %.3g frac>1 %.3g identical %.5f" % (mean, f2, f0, same))
+    assert mean <= 1e-3 and f2 <= 1e-3 and f0 <= 2e-4, (mean, f2, f0, same)
+
+
 def test_flow_clip_driver_single_rank(ctx, pkg, synth):
     """sequence.flow_clip (the multi-GPU clip driver) on one rank: loads each frame once, equals the pairwise call."""
     import importlib
@@ -203,6 +216,20 @@ def test_farneback_c5_8k_levels5_properties(ctx, pkg, synth):
     c = a[400:-400, 400:-400]
     epe = np.hypot(c[..., 0] - 2.5, c[..., 1] + 1.5)
     assert epe.mean() < 0.5 and np.median(epe) < 0.3, (epe.mean(), np.median(epe))
+
+
+def test_farneback_c5_8k_levels5_vs_oracle(ctx, pkg, oracle, synth):
+    """BASELINE.json config 5's frame pair (7680x4320, levels = 5 -> 6 scales) against the CPU oracle (about 35 s),
+    SURVEY.md 8c tolerances."""
+    h, w = 4320, 7680
+    par = pkg.FbParams(levels=5)
+    base = synth.gray(synth.texture(h, w, seed=2000))
+    nxt = synth.shift_bilinear(base, 2.5, -1.5)
+    got = ctx.farneback(base, nxt, par)
+    ref = oracle.farneback(base, nxt, levels=5)
+    mean, f2, f0, same = _stats(got, ref)
+    print("farneback 8K L5: mean %.3g frac>1e-2 %.3g frac>1 %.3g identical %.5f" % (mean, f2, f0, same))
+    assert mean <= 1e-3 and f2 <= 1e-3 and f0 <= 2e-4, (mean, f2, f0, same)
 
 
 def test_farneback_720p_polyn7_levels4(ctx, pkg, oracle, synth):
