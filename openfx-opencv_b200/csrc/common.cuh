@@ -43,7 +43,7 @@ struct ofxcv_ctx {
     // named device workspaces, grown on demand, reused between calls
     ofxcv_buf ws[72];
     // pinned host staging for the *_host entry points
-    ofxcv_buf pin[13];  // 0-3 internal staging, 4-11 ofxcv_scratch_pinned, 12 Dual TV-L1 stop flags
+    ofxcv_buf pin[14];  // 0-3 internal staging, 4-11 ofxcv_scratch_pinned, 12 Dual TV-L1 stop flags, 13 watershed round counters
     // per-family kernel timing (bench.py roofline numerator): events recorded on the launching stream
     bool timing = false;
     std::vector<ofxcv_timed_launch> timed[3];
@@ -71,7 +71,9 @@ struct ofxcv_ctx {
     cudaEvent_t tv_ev[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t tv_ctrl_off = 0;  // where the last ofxcv_tvl1_u8 put its control block inside WS_TV_ARENA
     int64_t inpaint_stats[4] = {0, 0, 0, 0};
-    int64_t watershed_stats[4] = {0, 0, 0, 0};
+    int64_t watershed_stats[4] = {0, 0, 0, 0};  // [0] pops (-1 = still on the device), [1] frames, [2] rounds, [3] passes of the parallel flood
+    std::vector<int> watershed_seq_frames;  // frames of the last call that ran on the one-thread flood
+    int64_t watershed_par_pops = 0;
 };
 
 int ofxcv_fail(ofxcv_ctx* ctx, cudaError_t e, const char* what);
@@ -147,6 +149,11 @@ static inline bool ofxcv_is_pinned(const void* p)
 
 static inline int ofxcv_div_up(int a, int b) { return (a + b - 1) / b; }
 
+// watershed_par.cu: exact intra-frame parallel flood of one prepared frame (see the header of that file); returns 1 when
+// the flood is degenerate and the one-thread kernel of watershed.cu should run instead (label map restored)
+int ofxcv_wsp_flood(ofxcv_ctx* ctx, cudaStream_t s, int32_t* m, ptrdiff_t pitch, const uint32_t* pix, int W, int H, int64_t* pops_out);
+size_t ofxcv_wsp_workspace_bytes(int W, int H, ptrdiff_t pitch);
+
 // workspace slot numbering
 enum {
     WS_FB_TMP = 0,   // row-blurred samples
@@ -203,6 +210,7 @@ enum {
     WS_FB3_FLOWB,
     WS_FB3_TOT,
     WS_TV_ARENA,  // Dual TV-L1: pyramids + J/A/P/U planes + control block, one allocation
+    WS_WSP_ARENA, // parallel watershed: claims, records, level queues, sort buffers, one allocation
     WS_COUNT
 };
 static_assert(WS_COUNT + 8 <= 72, "workspace slots (the last 8 are ofxcv_scratch_device)");

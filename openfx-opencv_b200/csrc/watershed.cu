@@ -15,6 +15,7 @@
 // Per-frame state: nxt int32 (intrusive FIFO link, every pixel is queued at most once) + pix u32, pitch = the
 // marker pitch.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -352,15 +353,53 @@ int ofxcv_watershed_u8c3_batch(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8
     dim3 grid(ofxcv_div_up(W, 256), H, nframes);
     ws_prepare<<<grid, 256, 0, s>>>(rgb, rgb_stride, rgb_frame_stride, markers, ms, m_frame, pix, st_frame, W, H);
     OFXCV_LAUNCH_CHECK(ctx);
-    ws_candidates<<<grid, 256, 0, s>>>(markers, ms, m_frame, pix, nxt, st_frame, W, H);
-    OFXCV_LAUNCH_CHECK(ctx);
-    ws_link<<<nframes, 1024, 0, s>>>(markers, ms, m_frame, nxt, st_frame, heads, W, H);
-    OFXCV_LAUNCH_CHECK(ctx);
-    ofxcv_time_begin(ctx, 2, s);
-    if (getenv("OFXCV_WS_FLOOD_V1")) ws_flood<<<nframes, 32, 0, s>>>(markers, ms, m_frame, pix, nxt, st_frame, heads, pops);
-    else ws_flood2<<<nframes, 32, 0, s>>>(markers, ms, m_frame, pix, nxt, st_frame, heads, pops);
-    ofxcv_time_end(ctx, 2, s);
-    OFXCV_LAUNCH_CHECK(ctx);
+    // Few frames: the exact intra-frame parallel flood (watershed_par.cu), one frame after the other on the whole GPU.
+    // Many frames: one thread per frame, all frames in flight (the parallel flood's ~5 frames/s is reached by the
+    // one-thread kernel from ~16 concurrent frames up).  OFXCV_WS_MODE=seq|par overrides.
+    const char* mode = getenv("OFXCV_WS_MODE");
+    const bool par = mode && !strcmp(mode, "par") ? true : mode && !strcmp(mode, "seq") ? false : nframes < 16;
+    std::vector<int> todo;  // frames left to the one-thread flood
+    int64_t par_pops = 0;
+    if (par) {
+        ofxcv_time_begin(ctx, 2, s);
+        for (int f = 0; f < nframes; f++) {
+            int64_t pops_f = 0;
+            const int st = ofxcv_wsp_flood(ctx, s, markers + f * m_frame, ms, pix + f * st_frame, W, H, &pops_f);
+            if (st < 0) return st;
+            if (st == 1) todo.push_back(f);
+            else par_pops += pops_f;
+        }
+        ofxcv_time_end(ctx, 2, s);
+    } else {
+        for (int f = 0; f < nframes; f++) todo.push_back(f);
+    }
+    ctx->watershed_par_pops = par_pops;
+    ctx->watershed_seq_frames.assign(todo.begin(), todo.end());
+    ctx->watershed_stats[0] = par_pops;
+    ctx->watershed_stats[1] = nframes;
+    if (todo.empty()) return OFXCV_OK;
+    ctx->watershed_stats[2] = ctx->watershed_stats[3] = 0;
+    if ((int)todo.size() == nframes) {
+        ws_candidates<<<grid, 256, 0, s>>>(markers, ms, m_frame, pix, nxt, st_frame, W, H);
+        OFXCV_LAUNCH_CHECK(ctx);
+        ws_link<<<nframes, 1024, 0, s>>>(markers, ms, m_frame, nxt, st_frame, heads, W, H);
+        OFXCV_LAUNCH_CHECK(ctx);
+        ofxcv_time_begin(ctx, 2, s);
+        if (getenv("OFXCV_WS_FLOOD_V1")) ws_flood<<<nframes, 32, 0, s>>>(markers, ms, m_frame, pix, nxt, st_frame, heads, pops);
+        else ws_flood2<<<nframes, 32, 0, s>>>(markers, ms, m_frame, pix, nxt, st_frame, heads, pops);
+        ofxcv_time_end(ctx, 2, s);
+        OFXCV_LAUNCH_CHECK(ctx);
+    } else {
+        for (int f : todo) {  // the degenerate frames of a small batch, one at a time
+            dim3 g1(ofxcv_div_up(W, 256), H, 1);
+            ws_candidates<<<g1, 256, 0, s>>>(markers + f * m_frame, ms, 0, pix + f * st_frame, nxt + f * st_frame, 0, W, H);
+            OFXCV_LAUNCH_CHECK(ctx);
+            ws_link<<<1, 1024, 0, s>>>(markers + f * m_frame, ms, 0, nxt + f * st_frame, 0, heads + (size_t)f * 512, W, H);
+            OFXCV_LAUNCH_CHECK(ctx);
+            ws_flood2<<<1, 32, 0, s>>>(markers + f * m_frame, ms, 0, pix + f * st_frame, nxt + f * st_frame, 0, heads + (size_t)f * 512, pops + f);
+            OFXCV_LAUNCH_CHECK(ctx);
+        }
+    }
     ctx->watershed_stats[0] = -1;  // resolved lazily by ofxcv_watershed_last_stats
     ctx->watershed_stats[1] = nframes;
     return OFXCV_OK;
@@ -382,8 +421,8 @@ int ofxcv_watershed_last_stats(const ofxcv_ctx* ctx_, int64_t stats[4])
         std::vector<unsigned long long> h(n);
         OFXCV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         OFXCV_CUDA(ctx, cudaMemcpy(h.data(), ctx->ws[WS_MISC2].p, (size_t)n * 8, cudaMemcpyDeviceToHost));
-        int64_t tot = 0;
-        for (int i = 0; i < n; i++) tot += (int64_t)h[i];
+        int64_t tot = ctx->watershed_par_pops;
+        for (int f : ctx->watershed_seq_frames) tot += (int64_t)h[f];
         ctx->watershed_stats[0] = tot;
     }
     for (int i = 0; i < 4; i++) stats[i] = ctx->watershed_stats[i];

@@ -1,0 +1,623 @@
+// Exact intra-frame parallel marker watershed for sm_100a: the flood of ONE frame, bit-identical to the sequential
+// Meyer flood of cv::watershed (BASELINE.json config 3; the segment plugin renders one frame per action,
+// /root/reference/opencv2fx/segment/segment.cpp:197-338), spread over the whole GPU.
+//
+// Why the ordered flood can be parallelised exactly.  cv::watershed always pops the head of the lowest non-empty FIFO
+// level (256 levels, first-parent level assignment, label decided at pop time), i.e. it runs
+//     Drain(b) = for c = 0..b:  while Q[c] not empty { pop head of Q[c]; Drain(c-1) }
+// so the pop sequence is a sequence of BLOCKS: one entry e popped from Q[c] while every lower level is empty, followed
+// by the complete sub-flood its pushes start at levels < c.  Blocks are ordered by (phase c, FIFO rank in Q[c]); the
+// entries a phase-c block appends to Q[c] form the next GENERATION of that phase, entries at levels > c wait for their
+// phase in push order.  On natural frames a 4K flood is a few hundred (phase, generation) ROUNDS of up to ~10^6 blocks;
+// 95 % of the blocks are the single pop, the sub-floods are small connected regions.
+//
+// A round runs all its blocks concurrently, one thread each, as ordered transactions:
+//   * every pixel a block pushes or pops is CLAIMED in a 64-bit word own[pixel] = rank << 32 | state with atomicMin /
+//     atomicCAS, so the lower rank (the earlier block of the sequential order) always wins; a block reads a neighbour
+//     as "state of the claim" if the claim's rank is <= its own, else as the committed label map (it must not see the
+//     future);
+//   * each pop records its OUTCOME (label, pixels pushed) and the neighbour states it took from its own block's earlier
+//     claims.  After the run a validation pass re-derives the outcome of every pop from the final claims of the lower
+//     ranks: a block with a pop whose outcome would now differ, or that lost a pixel of its sub-flood to a lower rank, is
+//     dirty -> its claims are retracted and it runs again (a queued-only pixel lost to a lower rank is simply struck
+//     from the record: nothing else of the block depended on it).  Rank 0 is right after the first pass, and by
+//     induction on the rank the iteration converges to exactly the sequential result (2-3 passes in practice);
+//   * commit: labels and IN_QUEUE marks go to the label map, the pushes at levels >= c are sorted by
+//     (level, rank, pop number inside the block, direction) = their sequential push order and appended to the level
+//     queues (plain arrays, every pixel is queued once).
+// The result does not depend on thread scheduling: the fixed point is unique.  A frame whose flood degenerates into
+// very many tiny rounds (adversarial serpentine images) is handed back to the one-thread flood (watershed.cu).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int WS_IN_QUEUE = -2;
+constexpr int WS_WSHED = -1;
+constexpr int WSP_PRIVATE = -3;  // claim state of a pixel queued below the phase level (it will be popped inside the block)
+constexpr unsigned long long WSP_EMPTY = ~0ull;
+constexpr int WSP_CHUNK = 4;  // sub-flood records are allocated WSP_CHUNK at a time
+
+struct __align__(16) WspRec {
+    int pixel;  // -1 = unused slot / retracted record
+    int rank;
+    int popseq;
+    int label;
+    int view[4];  // neighbour states at pop time; only the directions of the self mask are used by the validation
+    int next[4];  // private-queue link of the entry pushed in direction d: (record << 2 | direction) of the next entry of that level
+    unsigned char lvl[4];
+    unsigned pushmask;  // bits 0-3: directions pushed; bits 4-7: neighbour state came from a claim of this block (self mask)
+};
+static_assert(sizeof(WspRec) == 64, "record layout");
+
+struct WspCtl {  // device control block, copied to the host once per pass
+    unsigned long long nrec;  // record pool top
+    unsigned ndirty;
+    unsigned nout;        // live pushes at levels >= c (counted by the validation pass)
+    unsigned overflow;
+    unsigned ncand;
+    unsigned nlive;       // live records = pops of the round once no block is dirty
+    unsigned pad[3];
+};
+
+struct WspArgs {
+    int32_t* m;
+    const uint32_t* pix;
+    unsigned long long* own;
+    WspRec* rec;
+    const int* ent;
+    int* dirty;
+    WspCtl* ctl;
+    unsigned long long rec_cap;
+    int ms;  // pitch of m / pix / own in elements
+    int N;   // entries (blocks) of this round
+    int c;   // phase
+};
+
+__device__ __forceinline__ int wsp_diff(uint32_t a, uint32_t b)
+{
+    const uint32_t d = __vabsdiffu4(a, b);
+    return max((int)(d & 0xff), max((int)((d >> 8) & 0xff), (int)((d >> 16) & 0xff)));
+}
+
+__device__ __forceinline__ unsigned long long wsp_claim(unsigned rank, int state)
+{
+    return ((unsigned long long)rank << 32) | (unsigned)state;
+}
+
+__device__ __forceinline__ void wsp_flag_dirty(const WspArgs& a, unsigned r)
+{
+    if (atomicExch(a.dirty + r, 1) == 0) atomicAdd(&a.ctl->ndirty, 1u);
+}
+
+// ---- candidates: unlabelled 4-neighbours of a seed, keyed (level, row-major position) = OpenCV's initial push order --
+__global__ void __launch_bounds__(256) wsp_candidates(int32_t* __restrict__ m, const uint32_t* __restrict__ pix, int ms, int w, int h,
+                                                      unsigned long long* __restrict__ keys, int* __restrict__ vals, WspCtl* ctl)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x < 1 || y < 1 || x >= w - 1 || y >= h - 1) return;
+    const int o = y * ms + x;
+    if (m[o] != 0) return;
+    int idx = 256;
+    const uint32_t c = pix[o];
+    if (m[o - 1] > 0) idx = wsp_diff(c, pix[o - 1]);
+    if (m[o + 1] > 0) idx = min(idx, wsp_diff(c, pix[o + 1]));
+    if (m[o - ms] > 0) idx = min(idx, wsp_diff(c, pix[o - ms]));
+    if (m[o + ms] > 0) idx = min(idx, wsp_diff(c, pix[o + ms]));
+    if (idx == 256) return;
+    const unsigned k = atomicAdd(&ctl->ncand, 1u);
+    keys[k] = ((unsigned long long)idx << 56) | (unsigned)o;
+    vals[k] = o;
+}
+
+__global__ void __launch_bounds__(256) wsp_mark_queued(int32_t* __restrict__ m, const int* __restrict__ vals, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) m[vals[i]] = WS_IN_QUEUE;
+}
+
+// start[l] = first sorted key whose level (top byte) is >= l, l = 0..256
+__global__ void __launch_bounds__(288) wsp_bounds(const unsigned long long* __restrict__ keys, int n, int* __restrict__ start)
+{
+    const int l = threadIdx.x;
+    if (l > 256) return;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)(keys[mid] >> 56) < l) lo = mid + 1;
+        else hi = mid;
+    }
+    start[l] = lo;
+}
+
+struct WspSeg {
+    int src, cnt, dst;
+};
+__global__ void __launch_bounds__(256) wsp_gather(const int* __restrict__ Q, const WspSeg* __restrict__ segs, int* __restrict__ dst)
+{
+    const WspSeg s = segs[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.cnt; i += gridDim.x * blockDim.x) dst[s.dst + i] = Q[s.src + i];
+}
+
+// start of a round: every block is dirty, the record pool restarts above the N entry records
+__global__ void __launch_bounds__(256) wsp_round_init(int* __restrict__ dirty, int n, WspCtl* ctl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dirty[i] = 1;
+    if (i == 0) {
+        ctl->nrec = (unsigned long long)n;
+        ctl->overflow = 0;
+    }
+}
+
+// ---- one pass over the dirty blocks of a round: one thread = one block (entry pop + its sub-flood below level c) ------
+template <int NL>
+__global__ void __launch_bounds__(128) wsp_run(WspArgs a)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.N) return;
+    volatile int* dflag = a.dirty + q;
+    if (*dflag == 0) return;
+    *dflag = 0;
+    const unsigned uq = (unsigned)q;
+    const int e = a.ent[q];
+    const int ms = a.ms;
+    const int c = a.c;
+    int head[NL], tail[NL];
+    unsigned mask[NL / 32];
+#pragma unroll
+    for (int i = 0; i < NL / 32; i++) mask[i] = 0;
+    unsigned long long chunk = 0;  // next free sub-flood record; chunk_left of them remain reserved
+    int chunk_left = 0;
+    int popseq = 0;
+    int x = e;
+    unsigned long long ri = (unsigned long long)q;  // record of the pop being processed (the entry's record is slot q)
+    for (;;) {
+        // ---- the pop of x: neighbour states (one round of independent loads) ------------------------------------
+        int vis[4];
+        unsigned self = 0;
+        uint32_t cn[4];
+        const uint32_t cx = __ldg(a.pix + x);
+        const int off[4] = {-1, 1, -ms, ms};
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int y = x + off[d];
+            const unsigned long long v = __ldcg(a.own + y);
+            const int mm = __ldg(a.m + y);
+            cn[d] = __ldg(a.pix + y);
+            const unsigned r = (unsigned)(v >> 32);
+            const bool claimed = v != WSP_EMPTY;
+            vis[d] = (claimed && r <= uq) ? (int)(unsigned)v : mm;
+            if (claimed && r == uq) self |= 16u << d;
+        }
+        int lab = 0;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int t = vis[d];
+            if (t > 0) {
+                if (lab == 0) lab = t;
+                else if (t != lab) lab = WS_WSHED;
+            }
+        }
+        bool lost = false;
+        if (x == e) a.own[x] = wsp_claim(uq, lab);  // nobody else ever claims a queued entry
+        else lost = atomicCAS(a.own + x, wsp_claim(uq, WSP_PRIVATE), wsp_claim(uq, lab)) != wsp_claim(uq, WSP_PRIVATE);
+        WspRec* R = a.rec + ri;
+        unsigned pushmask = 0;
+        unsigned lv = 0;
+        int nx[4] = {-1, -1, -1, -1};
+        if (!lost && lab != WS_WSHED) {
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                if (vis[d] != 0) continue;
+                const int y = x + off[d];
+                const int l = wsp_diff(cx, cn[d]);
+                const unsigned long long old = atomicMin(a.own + y, wsp_claim(uq, l < c ? WSP_PRIVATE : WS_IN_QUEUE));
+                if (old != WSP_EMPTY) {
+                    const unsigned r = (unsigned)(old >> 32);
+                    if (r < uq) continue;  // a lower rank queued it in the meantime: not ours (the validation checks that this stays so)
+                    // stolen from a later block: if the pixel was part of its sub-flood that run is void (tell it now, it may
+                    // still be flooding); a pixel it had only queued is struck from its record by the validation
+                    if ((int)(unsigned)old != WS_IN_QUEUE) wsp_flag_dirty(a, r);
+                }
+                pushmask |= 1u << d;
+                lv |= (unsigned)l << (8 * d);
+                if (l < c) {  // private queue of this block
+                    const int id = (int)((ri << 2) | (unsigned)d);
+                    if (mask[l >> 5] & (1u << (l & 31))) {
+                        const int t = tail[l];
+                        if ((unsigned long long)(t >> 2) == ri) nx[t & 3] = id;
+                        else a.rec[t >> 2].next[t & 3] = id;
+                        tail[l] = id;
+                    } else {
+                        mask[l >> 5] |= 1u << (l & 31);
+                        head[l] = tail[l] = id;
+                    }
+                }
+            }
+        }
+        R->pixel = x;
+        R->rank = q;
+        R->popseq = popseq++;
+        R->label = lab;
+        *reinterpret_cast<int4*>(R->view) = make_int4(vis[0], vis[1], vis[2], vis[3]);
+        *reinterpret_cast<int4*>(R->next) = make_int4(nx[0], nx[1], nx[2], nx[3]);
+        *reinterpret_cast<unsigned*>(R->lvl) = lv;
+        R->pushmask = pushmask | self;
+        if (lost) {  // a lower rank took a pixel of our sub-flood while it waited in our queue
+            wsp_flag_dirty(a, uq);
+            break;
+        }
+        // ---- next pop: head of the lowest non-empty private level ------------------------------------------------
+        int l = -1;
+#pragma unroll
+        for (int i = NL / 32 - 1; i >= 0; i--)
+            if (mask[i]) l = i * 32 + __ffs(mask[i]) - 1;
+        if (l < 0) break;
+        if (*dflag) break;  // somebody stole from us: this run is void anyway
+        const int id = head[l];
+        const WspRec* P = a.rec + (id >> 2);
+        x = P->pixel + ((id & 3) == 0 ? -1 : (id & 3) == 1 ? 1 : (id & 3) == 2 ? -ms : ms);
+        const int nxt = (unsigned long long)(id >> 2) == ri ? nx[id & 3] : P->next[id & 3];
+        if (id == tail[l]) mask[l >> 5] &= ~(1u << (l & 31));
+        else head[l] = nxt;
+        if (chunk_left == 0) {
+            chunk = atomicAdd(&a.ctl->nrec, (unsigned long long)WSP_CHUNK);
+            chunk_left = WSP_CHUNK;
+            if (chunk + WSP_CHUNK > a.rec_cap) {
+                a.ctl->overflow = 1;
+                chunk_left = 0;
+                wsp_flag_dirty(a, uq);
+                break;
+            }
+        }
+        ri = chunk++;
+        chunk_left--;
+    }
+    for (; chunk_left > 0; chunk_left--) a.rec[chunk++].pixel = -1;
+}
+
+// ---- validation: one thread per record ---------------------------------------------------------------------------
+// the record kernels run over [0, pool top) with the top read on the device (no host round trip between run and validation)
+#define WSP_FOR_RECORDS(i)                                                                                        \
+    const unsigned long long wsp_top = min(a.ctl->nrec, a.rec_cap);                                               \
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < wsp_top;           \
+         i += (unsigned long long)gridDim.x * blockDim.x)
+
+__device__ __forceinline__ void wsp_validate_one(const WspArgs& a, unsigned long long i)
+{
+    WspRec* R = a.rec + i;
+    const int x = R->pixel;
+    if (x < 0) return;
+    const unsigned q = (unsigned)R->rank;
+    const int ms = a.ms;
+    const int off[4] = {-1, 1, -ms, ms};
+    const int4 view = *reinterpret_cast<const int4*>(R->view);
+    const int vw[4] = {view.x, view.y, view.z, view.w};
+    unsigned pm = R->pushmask;
+    const unsigned lv = *reinterpret_cast<const unsigned*>(R->lvl);
+    // the neighbour states this pop would see now: its own block's claims as recorded, lower ranks' claims as they ended
+    // up, everything else from the committed label map
+    int st[4];
+    unsigned long long cl[4];
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const int y = x + off[d];
+        const unsigned long long v = __ldcg(a.own + y);
+        cl[d] = v;
+        const unsigned r = (unsigned)(v >> 32);
+        st[d] = (pm & (16u << d)) ? vw[d] : (v != WSP_EMPTY && r < q) ? (int)(unsigned)v : __ldg(a.m + y);
+    }
+    int lab = 0;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const int t = st[d];
+        if (t > 0) {
+            if (lab == 0) lab = t;
+            else if (t != lab) lab = WS_WSHED;
+        }
+    }
+    bool bad = lab != R->label;
+    const unsigned long long vx = __ldcg(a.own + x);
+    if (vx == WSP_EMPTY || (unsigned)(vx >> 32) != q) bad = true;  // the popped pixel itself was taken by a lower rank
+    unsigned nout = 0;
+    bool repaired = false;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const bool should = lab != WS_WSHED && st[d] == 0;
+        const bool has = (pm >> d) & 1u;
+        const int l = (int)((lv >> (8 * d)) & 0xff);
+        if (has) {
+            const unsigned r = (unsigned)(cl[d] >> 32);
+            if (cl[d] != WSP_EMPTY && r == q) {
+                if (!should) bad = true;
+                else if (l >= a.c) nout++;
+            } else if (cl[d] != WSP_EMPTY && r < q && l >= a.c) {
+                pm &= ~(1u << d);  // a lower rank queued it first: in the sequential order this pop finds it queued
+                repaired = true;
+            } else {
+                bad = true;
+            }
+        } else if (should) {
+            bad = true;  // e.g. the lower claim that kept us from queueing it has been retracted
+        }
+    }
+    if (repaired) R->pushmask = pm;
+    if (bad) wsp_flag_dirty(a, q);
+    if (nout) atomicAdd(&a.ctl->nout, nout);
+    atomicAdd(&a.ctl->nlive, 1u);
+}
+
+__global__ void __launch_bounds__(256) wsp_validate(WspArgs a)
+{
+    WSP_FOR_RECORDS(i) wsp_validate_one(a, i);
+}
+
+// ---- retraction of the records of dirty blocks --------------------------------------------------------------------
+__device__ __forceinline__ void wsp_retract_one(const WspArgs& a, unsigned long long i)
+{
+    WspRec* R = a.rec + i;
+    const int x = R->pixel;
+    if (x < 0) return;
+    const unsigned q = (unsigned)R->rank;
+    if (!a.dirty[q]) return;
+    const int ms = a.ms;
+    const int off[4] = {-1, 1, -ms, ms};
+    const unsigned pm = R->pushmask;
+    auto release = [&](int y) {
+        const unsigned long long v = __ldcg(a.own + y);
+        if (v != WSP_EMPTY && (unsigned)(v >> 32) == q) atomicCAS(a.own + y, v, WSP_EMPTY);
+    };
+    release(x);
+#pragma unroll
+    for (int d = 0; d < 4; d++)
+        if (pm & (1u << d)) release(x + off[d]);
+    R->pixel = -1;
+}
+
+__global__ void __launch_bounds__(256) wsp_retract(WspArgs a)
+{
+    WSP_FOR_RECORDS(i) wsp_retract_one(a, i);
+}
+
+// ---- commit ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wsp_commit_one(const WspArgs& a, unsigned long long i, unsigned long long* __restrict__ keys,
+                                               int* __restrict__ vals, unsigned* __restrict__ nkeys)
+{
+    const WspRec* R = a.rec + i;
+    const int x = R->pixel;
+    if (x < 0) return;
+    const unsigned q = (unsigned)R->rank;
+    const int ms = a.ms;
+    const int off[4] = {-1, 1, -ms, ms};
+    a.m[x] = R->label;
+    const unsigned pm = R->pushmask;
+    const unsigned lv = *reinterpret_cast<const unsigned*>(R->lvl);
+    const unsigned seq = (unsigned)R->popseq;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        if (!(pm & (1u << d))) continue;
+        const int y = x + off[d];
+        const int l = (int)((lv >> (8 * d)) & 0xff);
+        if (l >= a.c) {  // stays queued after this round
+            a.m[y] = WS_IN_QUEUE;
+            const unsigned k = atomicAdd(nkeys, 1u);
+            keys[k] = ((unsigned long long)l << 56) | ((unsigned long long)q << 29) | ((unsigned long long)seq << 2) | (unsigned)d;
+            vals[k] = y;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) wsp_commit(WspArgs a, unsigned long long* __restrict__ keys, int* __restrict__ vals,
+                                                  unsigned* __restrict__ nkeys)
+{
+    WSP_FOR_RECORDS(i) wsp_commit_one(a, i, keys, vals, nkeys);
+}
+
+__device__ __forceinline__ void wsp_clear_one(const WspArgs& a, unsigned long long i)
+{
+    const WspRec* R = a.rec + i;
+    const int x = R->pixel;
+    if (x < 0) return;
+    const int ms = a.ms;
+    const int off[4] = {-1, 1, -ms, ms};
+    a.own[x] = WSP_EMPTY;
+    const unsigned pm = R->pushmask;
+#pragma unroll
+    for (int d = 0; d < 4; d++)
+        if (pm & (1u << d)) a.own[x + off[d]] = WSP_EMPTY;
+}
+
+__global__ void __launch_bounds__(256) wsp_clear_claims(WspArgs a)
+{
+    WSP_FOR_RECORDS(i) wsp_clear_one(a, i);
+}
+
+size_t wsp_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+// key layout of a queued push: level 8 | rank 27 | pop number inside the block 27 | direction 2
+constexpr int WSP_RANK_BITS = 27;
+
+size_t ofxcv_wsp_workspace_bytes(int W, int H, ptrdiff_t pitch)
+{
+    const size_t st = (size_t)pitch * H;
+    size_t sort_tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr,
+                                    (int)st, 0, 64, (cudaStream_t)0);
+    (void)W;
+    return wsp_align(st * 8) + wsp_align((st + 65536) * sizeof(WspRec)) + 3 * wsp_align(st * 4 + 4096) + 2 * wsp_align(st * 8) +
+           wsp_align(st * 4) + wsp_align(sort_tmp) + wsp_align(st * 4) + 65536;
+}
+
+// Flood of one prepared frame (border = -1, negatives = 0, pix = packed RGBX; what ws_prepare leaves).  Blocking: the
+// round loop reads a few counters back per pass.  Returns OFXCV_OK, an error, or 1 = "degenerate flood, the label map
+// has been restored to its prepared state: run the one-thread flood instead".
+int ofxcv_wsp_flood(ofxcv_ctx* ctx, cudaStream_t s, int32_t* m, ptrdiff_t pitch, const uint32_t* pix, int W, int H, int64_t* pops_out)
+{
+    const size_t st = (size_t)pitch * H;
+    if (st >= ((size_t)1 << WSP_RANK_BITS)) return 1;  // ranks / pop numbers would not fit the sort key
+    size_t sort_tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr,
+                                    (int*)nullptr, (int)st, 0, 64, s);
+    const size_t rec_cap = st + 65536;
+    char* arena = (char*)ofxcv_ws(ctx, WS_WSP_ARENA, ofxcv_wsp_workspace_bytes(W, H, pitch));
+    WspCtl* hctl = (WspCtl*)ofxcv_pin(ctx, 13, 4096);
+    if (!arena || !hctl) return OFXCV_ERR_MEMORY;
+    int* hstart = (int*)(hctl + 1);  // 257 level boundaries
+    size_t o = 0;
+    auto carve = [&](size_t bytes) {
+        char* p = arena + o;
+        o += wsp_align(bytes);
+        return p;
+    };
+    unsigned long long* own = (unsigned long long*)carve(st * 8);
+    WspRec* rec = (WspRec*)carve(rec_cap * sizeof(WspRec));
+    int* Q = (int*)carve(st * 4 + 4096);
+    int* ent0 = (int*)carve(st * 4 + 4096);
+    int* dirty = (int*)carve(st * 4 + 4096);
+    unsigned long long* keys = (unsigned long long*)carve(st * 8);
+    unsigned long long* keys2 = (unsigned long long*)carve(st * 8);
+    int* vals = (int*)carve(st * 4);
+    void* sort_tmp = carve(sort_tmp_bytes);
+    int32_t* backup = (int32_t*)carve(st * 4);
+    WspCtl* ctl = (WspCtl*)carve(4096);
+    int* dstart = (int*)(ctl + 1);
+    WspSeg* dsegs = (WspSeg*)carve(32768);
+    constexpr int MAX_GATHER = 32768 / (int)sizeof(WspSeg);
+
+    OFXCV_CUDA(ctx, cudaMemcpyAsync(backup, m, st * 4, cudaMemcpyDeviceToDevice, s));
+    OFXCV_CUDA(ctx, cudaMemsetAsync(own, 0xff, st * 8, s));
+    OFXCV_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(WspCtl), s));
+    auto restore = [&]() -> int {
+        cudaMemcpyAsync(m, backup, st * 4, cudaMemcpyDeviceToDevice, s);
+        return 1;
+    };
+    auto readback = [&](size_t bytes) -> int {
+        OFXCV_CUDA(ctx, cudaMemcpyAsync(hctl, ctl, bytes, cudaMemcpyDeviceToHost, s));
+        OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+        return OFXCV_OK;
+    };
+    // per-level lists of queue segments (offset into Q, count), in push order
+    std::vector<std::pair<int, int>> segs[256];
+    size_t qtop = 0;
+    auto append_sorted = [&](int n, int cmin, int* next_off, int* next_cnt) -> int {
+        // keys/vals[0..n) -> sorted by key, values land at Q + qtop; registers one segment per level present
+        OFXCV_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp, sort_tmp_bytes, keys, keys2, vals, Q + qtop, n, 0, 64, s));
+        ctx->launches += 2;
+        wsp_bounds<<<1, 288, 0, s>>>(keys2, n, dstart);
+        OFXCV_LAUNCH_CHECK(ctx);
+        OFXCV_CUDA(ctx, cudaMemcpyAsync(hstart, dstart, 257 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+        for (int l = 0; l < 256; l++) {
+            const int cnt = hstart[l + 1] - hstart[l];
+            if (cnt <= 0) continue;
+            if (l == cmin && next_off) {
+                *next_off = (int)qtop + hstart[l];
+                *next_cnt = cnt;
+            } else {
+                segs[l].push_back({(int)qtop + hstart[l], cnt});
+            }
+        }
+        qtop += (size_t)n;
+        return OFXCV_OK;
+    };
+
+    // ---- initial candidates ---------------------------------------------------------------------------------------
+    wsp_candidates<<<dim3(ofxcv_div_up(W, 256), H), 256, 0, s>>>(m, pix, (int)pitch, W, H, keys, vals, ctl);
+    OFXCV_LAUNCH_CHECK(ctx);
+    int st_ = readback(sizeof(WspCtl));
+    if (st_ < 0) return st_;
+    const int ncand = (int)hctl->ncand;
+    if (ncand > 0) {
+        wsp_mark_queued<<<ofxcv_div_up(ncand, 256), 256, 0, s>>>(m, vals, ncand);
+        OFXCV_LAUNCH_CHECK(ctx);
+        if ((st_ = append_sorted(ncand, -1, nullptr, nullptr)) < 0) return st_;
+    }
+
+    WspArgs a;
+    a.m = m;
+    a.pix = pix;
+    a.own = own;
+    a.rec = rec;
+    a.dirty = dirty;
+    a.ctl = ctl;
+    a.rec_cap = rec_cap;
+    a.ms = (int)pitch;
+    long rounds = 0, passes = 0;
+    int64_t pops = 0;
+    const int rgrid = ctx->num_sms * 8;  // grid of the record kernels (grid-stride over the pool)
+    for (int c = 0; c < 256; c++) {
+        if (segs[c].empty()) continue;
+        // generation 0 of phase c: every segment queued for this level so far, in push order
+        const int* ent = nullptr;
+        int N = 0;
+        if (segs[c].size() == 1) {
+            ent = Q + segs[c][0].first;
+            N = segs[c][0].second;
+        } else {
+            std::vector<WspSeg> hs;
+            for (auto& sg : segs[c]) {
+                hs.push_back({sg.first, sg.second, N});
+                N += sg.second;
+            }
+            for (size_t b = 0; b < hs.size(); b += MAX_GATHER) {
+                const int nb = (int)std::min(hs.size() - b, (size_t)MAX_GATHER);
+                OFXCV_CUDA(ctx, cudaMemcpyAsync(dsegs, hs.data() + b, nb * sizeof(WspSeg), cudaMemcpyHostToDevice, s));
+                wsp_gather<<<dim3(32, nb), 256, 0, s>>>(Q, dsegs, ent0);
+                OFXCV_LAUNCH_CHECK(ctx);
+                OFXCV_CUDA(ctx, cudaStreamSynchronize(s));  // hs is pageable host memory, dsegs is reused
+            }
+            ent = ent0;
+        }
+        segs[c].clear();
+        while (N > 0) {
+            // a flood that degenerates into very many tiny rounds is faster on the one-thread kernel
+            if (++rounds >= 2048 && (rounds & 1023) == 0 && pops < rounds * 256) return restore();
+            a.ent = ent;
+            a.N = N;
+            a.c = c;
+            wsp_round_init<<<ofxcv_div_up(N, 256), 256, 0, s>>>(dirty, N, ctl);
+            OFXCV_LAUNCH_CHECK(ctx);
+            for (bool first = true;; first = false) {
+                passes++;
+                if (!first) {
+                    wsp_retract<<<rgrid, 256, 0, s>>>(a);
+                    OFXCV_LAUNCH_CHECK(ctx);
+                }
+                // counters of the pass (the pool top carries over)
+                OFXCV_CUDA(ctx, cudaMemsetAsync(&ctl->ndirty, 0, 2 * sizeof(unsigned), s));
+                OFXCV_CUDA(ctx, cudaMemsetAsync(&ctl->nlive, 0, sizeof(unsigned), s));
+                if (c <= 32) wsp_run<32><<<ofxcv_div_up(N, 128), 128, 0, s>>>(a);
+                else wsp_run<256><<<ofxcv_div_up(N, 128), 128, 0, s>>>(a);
+                OFXCV_LAUNCH_CHECK(ctx);
+                wsp_validate<<<rgrid, 256, 0, s>>>(a);
+                OFXCV_LAUNCH_CHECK(ctx);
+                if ((st_ = readback(sizeof(WspCtl))) < 0) return st_;
+                if (hctl->overflow) return restore();
+                if (hctl->ndirty == 0) break;
+            }
+            const int nout = (int)hctl->nout;
+            pops += (int64_t)hctl->nlive;
+            int next_off = 0, next_cnt = 0;
+            OFXCV_CUDA(ctx, cudaMemsetAsync(&ctl->nout, 0, sizeof(unsigned), s));
+            wsp_commit<<<rgrid, 256, 0, s>>>(a, keys, vals, &ctl->nout);
+            OFXCV_LAUNCH_CHECK(ctx);
+            wsp_clear_claims<<<rgrid, 256, 0, s>>>(a);
+            OFXCV_LAUNCH_CHECK(ctx);
+            if (nout > 0) {
+                if (qtop + (size_t)nout > st + 1024) return restore();
+                if ((st_ = append_sorted(nout, c, &next_off, &next_cnt)) < 0) return st_;
+            }
+            ent = Q + next_off;
+            N = next_cnt;
+        }
+    }
+    if (pops_out) *pops_out = pops;
+    ctx->watershed_stats[2] = rounds;
+    ctx->watershed_stats[3] = passes;
+    return OFXCV_OK;
+}
