@@ -37,7 +37,7 @@ constexpr int WS_IN_QUEUE = -2;
 constexpr int WS_WSHED = -1;
 constexpr int WSP_PRIVATE = -3;  // claim state of a pixel queued below the phase level (it will be popped inside the block)
 constexpr unsigned long long WSP_EMPTY = ~0ull;
-constexpr int WSP_CHUNK = 4;  // sub-flood records are allocated WSP_CHUNK at a time
+constexpr int WSP_CHUNK0 = 4, WSP_CHUNK = 16;  // sub-flood records are allocated in chunks: the first one small, then WSP_CHUNK
 
 struct __align__(16) WspRec {
     int pixel;  // -1 = unused slot / retracted record
@@ -45,11 +45,11 @@ struct __align__(16) WspRec {
     int popseq;
     int label;
     int view[4];  // neighbour states at pop time; only the directions of the self mask are used by the validation
-    int next[4];  // private-queue link of the entry pushed in direction d: (record << 2 | direction) of the next entry of that level
     unsigned char lvl[4];
     unsigned pushmask;  // bits 0-3: directions pushed; bits 4-7: neighbour state came from a claim of this block (self mask)
+    int pad[2];
 };
-static_assert(sizeof(WspRec) == 64, "record layout");
+static_assert(sizeof(WspRec) == 48, "record layout");
 
 struct WspCtl {  // device control block, copied to the host once per pass
     unsigned long long nrec;  // record pool top
@@ -65,9 +65,11 @@ struct WspArgs {
     int32_t* m;
     const uint32_t* pix;
     unsigned long long* own;
+    unsigned long long* lnk;  // private-queue link per pixel: rank << 32 | next pixel of the same level in that block's queue
     WspRec* rec;
     const int* ent;
-    int* dirty;
+    int* dirty;  // set by whoever invalidates a block (a steal during the run, the validation)
+    int* runf;   // the blocks this pass re-runs: dirty latched at the start of the pass
     WspCtl* ctl;
     unsigned long long rec_cap;
     int ms;  // pitch of m / pix / own in elements
@@ -141,14 +143,28 @@ __global__ void __launch_bounds__(256) wsp_gather(const int* __restrict__ Q, con
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.cnt; i += gridDim.x * blockDim.x) dst[s.dst + i] = Q[s.src + i];
 }
 
-// start of a round: every block is dirty, the record pool restarts above the N entry records
-__global__ void __launch_bounds__(256) wsp_round_init(int* __restrict__ dirty, int n, WspCtl* ctl)
+// start of a round: every block runs, the record pool restarts above the N entry records
+__global__ void __launch_bounds__(256) wsp_round_init(int* __restrict__ dirty, int* __restrict__ runf, int n, WspCtl* ctl)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dirty[i] = 1;
+    if (i < n) {
+        dirty[i] = 0;
+        runf[i] = 1;
+    }
     if (i == 0) {
         ctl->nrec = (unsigned long long)n;
         ctl->overflow = 0;
+    }
+}
+
+// start of a later pass: the blocks flagged so far are the ones whose records are retracted and that run again; flags
+// raised from now on (steals during the run, the validation) belong to the next pass
+__global__ void __launch_bounds__(256) wsp_latch(int* __restrict__ dirty, int* __restrict__ runf, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        runf[i] = dirty[i];
+        dirty[i] = 0;
     }
 }
 
@@ -158,13 +174,14 @@ __global__ void __launch_bounds__(128) wsp_run(WspArgs a)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= a.N) return;
-    volatile int* dflag = a.dirty + q;
-    if (*dflag == 0) return;
-    *dflag = 0;
+    if (a.runf[q] == 0) return;
+    volatile int* dflag = a.dirty + q;  // raised by a lower rank that takes a pixel of our sub-flood
     const unsigned uq = (unsigned)q;
     const int e = a.ent[q];
     const int ms = a.ms;
     const int c = a.c;
+    // private queue of the sub-flood: one FIFO per level < c, heads / tails are pixels, the links live in lnk[pixel] (a
+    // pixel is in at most one private queue at a time: the one of the block that holds its claim)
     int head[NL], tail[NL];
     unsigned mask[NL / 32];
 #pragma unroll
@@ -173,13 +190,23 @@ __global__ void __launch_bounds__(128) wsp_run(WspArgs a)
     int chunk_left = 0;
     int popseq = 0;
     int x = e;
+    int lx = -1;            // level x was dequeued from, when its successor still has to become the head (-1: nothing pending)
     unsigned long long ri = (unsigned long long)q;  // record of the pop being processed (the entry's record is slot q)
     for (;;) {
-        // ---- the pop of x: neighbour states (one round of independent loads) ------------------------------------
+        // ---- the pop of x: one round of independent loads ------------------------------------------------------
+        if (x != e) {
+            if (chunk_left == 0) {
+                const int n = popseq == 1 ? WSP_CHUNK0 : WSP_CHUNK;
+                chunk = atomicAdd(&a.ctl->nrec, (unsigned long long)n);
+                chunk_left = n;
+            }
+        }
         int vis[4];
         unsigned self = 0;
         uint32_t cn[4];
         const uint32_t cx = __ldg(a.pix + x);
+        const unsigned long long succ = lx >= 0 ? __ldcg(a.lnk + x) : ((unsigned long long)uq << 32);
+        const int stolen = x != e ? *dflag : 0;
         const int off[4] = {-1, 1, -ms, ms};
 #pragma unroll
         for (int d = 0; d < 4; d++) {
@@ -192,6 +219,20 @@ __global__ void __launch_bounds__(128) wsp_run(WspArgs a)
             vis[d] = (claimed && r <= uq) ? (int)(unsigned)v : mm;
             if (claimed && r == uq) self |= 16u << d;
         }
+        if (x != e) {
+            const bool torn = (unsigned)(succ >> 32) != uq;  // the link of x is not ours: x was taken and re-queued by a lower rank
+            if (chunk + chunk_left > a.rec_cap || stolen || torn) {  // pool exhausted, or somebody stole from us: this run is void
+                if (!stolen && !torn) {
+                    a.ctl->overflow = 1;
+                    chunk_left = 0;
+                }
+                wsp_flag_dirty(a, uq);
+                break;
+            }
+            ri = chunk++;
+            chunk_left--;
+        }
+        if (lx >= 0) head[lx] = (int)(unsigned)succ;
         int lab = 0;
 #pragma unroll
         for (int d = 0; d < 4; d++) {
@@ -201,14 +242,12 @@ __global__ void __launch_bounds__(128) wsp_run(WspArgs a)
                 else if (t != lab) lab = WS_WSHED;
             }
         }
-        bool lost = false;
+        unsigned long long cas_old = wsp_claim(uq, WSP_PRIVATE);
         if (x == e) a.own[x] = wsp_claim(uq, lab);  // nobody else ever claims a queued entry
-        else lost = atomicCAS(a.own + x, wsp_claim(uq, WSP_PRIVATE), wsp_claim(uq, lab)) != wsp_claim(uq, WSP_PRIVATE);
-        WspRec* R = a.rec + ri;
+        else cas_old = atomicCAS(a.own + x, wsp_claim(uq, WSP_PRIVATE), wsp_claim(uq, lab));
         unsigned pushmask = 0;
         unsigned lv = 0;
-        int nx[4] = {-1, -1, -1, -1};
-        if (!lost && lab != WS_WSHED) {
+        if (lab != WS_WSHED) {
 #pragma unroll
             for (int d = 0; d < 4; d++) {
                 if (vis[d] != 0) continue;
@@ -224,29 +263,23 @@ __global__ void __launch_bounds__(128) wsp_run(WspArgs a)
                 }
                 pushmask |= 1u << d;
                 lv |= (unsigned)l << (8 * d);
-                if (l < c) {  // private queue of this block
-                    const int id = (int)((ri << 2) | (unsigned)d);
+                if (l < c) {
                     if (mask[l >> 5] & (1u << (l & 31))) {
-                        const int t = tail[l];
-                        if ((unsigned long long)(t >> 2) == ri) nx[t & 3] = id;
-                        else a.rec[t >> 2].next[t & 3] = id;
-                        tail[l] = id;
+                        // atomicMin: if the tail has meanwhile been taken by a lower rank, its own link must survive ours
+                        atomicMin(a.lnk + tail[l], ((unsigned long long)uq << 32) | (unsigned)y);
+                        tail[l] = y;
                     } else {
                         mask[l >> 5] |= 1u << (l & 31);
-                        head[l] = tail[l] = id;
+                        head[l] = tail[l] = y;
                     }
                 }
             }
         }
-        R->pixel = x;
-        R->rank = q;
-        R->popseq = popseq++;
-        R->label = lab;
+        WspRec* R = a.rec + ri;
+        *reinterpret_cast<int4*>(&R->pixel) = make_int4(x, q, popseq++, lab);
         *reinterpret_cast<int4*>(R->view) = make_int4(vis[0], vis[1], vis[2], vis[3]);
-        *reinterpret_cast<int4*>(R->next) = make_int4(nx[0], nx[1], nx[2], nx[3]);
-        *reinterpret_cast<unsigned*>(R->lvl) = lv;
-        R->pushmask = pushmask | self;
-        if (lost) {  // a lower rank took a pixel of our sub-flood while it waited in our queue
+        *reinterpret_cast<uint2*>(R->lvl) = make_uint2(lv, pushmask | self);
+        if (cas_old != wsp_claim(uq, WSP_PRIVATE)) {  // a lower rank took this pixel while it waited in our queue
             wsp_flag_dirty(a, uq);
             break;
         }
@@ -256,25 +289,13 @@ __global__ void __launch_bounds__(128) wsp_run(WspArgs a)
         for (int i = NL / 32 - 1; i >= 0; i--)
             if (mask[i]) l = i * 32 + __ffs(mask[i]) - 1;
         if (l < 0) break;
-        if (*dflag) break;  // somebody stole from us: this run is void anyway
-        const int id = head[l];
-        const WspRec* P = a.rec + (id >> 2);
-        x = P->pixel + ((id & 3) == 0 ? -1 : (id & 3) == 1 ? 1 : (id & 3) == 2 ? -ms : ms);
-        const int nxt = (unsigned long long)(id >> 2) == ri ? nx[id & 3] : P->next[id & 3];
-        if (id == tail[l]) mask[l >> 5] &= ~(1u << (l & 31));
-        else head[l] = nxt;
-        if (chunk_left == 0) {
-            chunk = atomicAdd(&a.ctl->nrec, (unsigned long long)WSP_CHUNK);
-            chunk_left = WSP_CHUNK;
-            if (chunk + WSP_CHUNK > a.rec_cap) {
-                a.ctl->overflow = 1;
-                chunk_left = 0;
-                wsp_flag_dirty(a, uq);
-                break;
-            }
+        x = head[l];
+        if (x == tail[l]) {
+            mask[l >> 5] &= ~(1u << (l & 31));
+            lx = -1;
+        } else {
+            lx = l;  // head[l] becomes lnk[x], which is loaded with the neighbourhood of x
         }
-        ri = chunk++;
-        chunk_left--;
     }
     for (; chunk_left > 0; chunk_left--) a.rec[chunk++].pixel = -1;
 }
@@ -362,18 +383,22 @@ __device__ __forceinline__ void wsp_retract_one(const WspArgs& a, unsigned long 
     const int x = R->pixel;
     if (x < 0) return;
     const unsigned q = (unsigned)R->rank;
-    if (!a.dirty[q]) return;
+    if (!a.runf[q]) return;
     const int ms = a.ms;
     const int off[4] = {-1, 1, -ms, ms};
     const unsigned pm = R->pushmask;
-    auto release = [&](int y) {
-        const unsigned long long v = __ldcg(a.own + y);
-        if (v != WSP_EMPTY && (unsigned)(v >> 32) == q) atomicCAS(a.own + y, v, WSP_EMPTY);
+    const unsigned lv = *reinterpret_cast<const unsigned*>(R->lvl);
+    auto release = [&](unsigned long long* p) {  // only what is (still) ours
+        const unsigned long long v = __ldcg(p);
+        if (v != WSP_EMPTY && (unsigned)(v >> 32) == q) atomicCAS(p, v, WSP_EMPTY);
     };
-    release(x);
+    release(a.own + x);
 #pragma unroll
     for (int d = 0; d < 4; d++)
-        if (pm & (1u << d)) release(x + off[d]);
+        if (pm & (1u << d)) {
+            release(a.own + x + off[d]);
+            if ((int)((lv >> (8 * d)) & 0xff) < a.c) release(a.lnk + x + off[d]);
+        }
     R->pixel = -1;
 }
 
@@ -425,9 +450,13 @@ __device__ __forceinline__ void wsp_clear_one(const WspArgs& a, unsigned long lo
     const int off[4] = {-1, 1, -ms, ms};
     a.own[x] = WSP_EMPTY;
     const unsigned pm = R->pushmask;
+    const unsigned lv = *reinterpret_cast<const unsigned*>(R->lvl);
 #pragma unroll
     for (int d = 0; d < 4; d++)
-        if (pm & (1u << d)) a.own[x + off[d]] = WSP_EMPTY;
+        if (pm & (1u << d)) {
+            a.own[x + off[d]] = WSP_EMPTY;
+            if ((int)((lv >> (8 * d)) & 0xff) < a.c) a.lnk[x + off[d]] = WSP_EMPTY;
+        }
 }
 
 __global__ void __launch_bounds__(256) wsp_clear_claims(WspArgs a)
@@ -449,7 +478,7 @@ size_t ofxcv_wsp_workspace_bytes(int W, int H, ptrdiff_t pitch)
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr,
                                     (int)st, 0, 64, (cudaStream_t)0);
     (void)W;
-    return wsp_align(st * 8) + wsp_align((st + 65536) * sizeof(WspRec)) + 3 * wsp_align(st * 4 + 4096) + 2 * wsp_align(st * 8) +
+    return 2 * wsp_align(st * 8) + wsp_align((st + 65536) * sizeof(WspRec)) + 4 * wsp_align(st * 4 + 4096) + 2 * wsp_align(st * 8) +
            wsp_align(st * 4) + wsp_align(sort_tmp) + wsp_align(st * 4) + 65536;
 }
 
@@ -475,10 +504,12 @@ int ofxcv_wsp_flood(ofxcv_ctx* ctx, cudaStream_t s, int32_t* m, ptrdiff_t pitch,
         return p;
     };
     unsigned long long* own = (unsigned long long*)carve(st * 8);
+    unsigned long long* lnk = (unsigned long long*)carve(st * 8);
     WspRec* rec = (WspRec*)carve(rec_cap * sizeof(WspRec));
     int* Q = (int*)carve(st * 4 + 4096);
     int* ent0 = (int*)carve(st * 4 + 4096);
     int* dirty = (int*)carve(st * 4 + 4096);
+    int* runf = (int*)carve(st * 4 + 4096);
     unsigned long long* keys = (unsigned long long*)carve(st * 8);
     unsigned long long* keys2 = (unsigned long long*)carve(st * 8);
     int* vals = (int*)carve(st * 4);
@@ -491,6 +522,7 @@ int ofxcv_wsp_flood(ofxcv_ctx* ctx, cudaStream_t s, int32_t* m, ptrdiff_t pitch,
 
     OFXCV_CUDA(ctx, cudaMemcpyAsync(backup, m, st * 4, cudaMemcpyDeviceToDevice, s));
     OFXCV_CUDA(ctx, cudaMemsetAsync(own, 0xff, st * 8, s));
+    OFXCV_CUDA(ctx, cudaMemsetAsync(lnk, 0xff, st * 8, s));
     OFXCV_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(WspCtl), s));
     auto restore = [&]() -> int {
         cudaMemcpyAsync(m, backup, st * 4, cudaMemcpyDeviceToDevice, s);
@@ -542,8 +574,10 @@ int ofxcv_wsp_flood(ofxcv_ctx* ctx, cudaStream_t s, int32_t* m, ptrdiff_t pitch,
     a.m = m;
     a.pix = pix;
     a.own = own;
+    a.lnk = lnk;
     a.rec = rec;
     a.dirty = dirty;
+    a.runf = runf;
     a.ctl = ctl;
     a.rec_cap = rec_cap;
     a.ms = (int)pitch;
@@ -580,11 +614,13 @@ int ofxcv_wsp_flood(ofxcv_ctx* ctx, cudaStream_t s, int32_t* m, ptrdiff_t pitch,
             a.ent = ent;
             a.N = N;
             a.c = c;
-            wsp_round_init<<<ofxcv_div_up(N, 256), 256, 0, s>>>(dirty, N, ctl);
+            wsp_round_init<<<ofxcv_div_up(N, 256), 256, 0, s>>>(dirty, runf, N, ctl);
             OFXCV_LAUNCH_CHECK(ctx);
             for (bool first = true;; first = false) {
                 passes++;
                 if (!first) {
+                    wsp_latch<<<ofxcv_div_up(N, 256), 256, 0, s>>>(dirty, runf, N);
+                    OFXCV_LAUNCH_CHECK(ctx);
                     wsp_retract<<<rgrid, 256, 0, s>>>(a);
                     OFXCV_LAUNCH_CHECK(ctx);
                 }
