@@ -48,11 +48,7 @@ constexpr unsigned WSP_COMMITTED = 0xffffffffu;
 constexpr unsigned long long WSP_EMPTY_WORD = ~0ull;  // tag COMMITTED: "no claim there"
 constexpr int WSP_CHUNK0 = 4, WSP_CHUNK = 16;  // sub-flood records are allocated in chunks: the first one small, then WSP_CHUNK
 
-struct __align__(16) WspPx {
-    unsigned long long own;
-    uint32_t pix;  // packed RGBX
-    uint32_t pad;
-};
+typedef unsigned long long WspPx;  // the claim word of a pixel (the packed colours stay in their own plane: read-only, L1-cacheable)
 
 struct __align__(16) WspRec {
     int pixel;  // -1 = unused slot / retracted record
@@ -78,6 +74,7 @@ struct WspCtl {  // device control block, copied to the host once per pass
 
 struct WspArgs {
     WspPx* px;
+    const uint32_t* pix;  // packed RGBX
     WspRec* rec;
     const int* ent;
     int* dirty;  // set by whoever invalidates a block (a steal during the run, the validation)
@@ -115,25 +112,20 @@ __device__ __forceinline__ void wsp_flag_dirty(const WspArgs& a, unsigned r)
 
 __device__ __forceinline__ unsigned long long wsp_ld_own(const WspPx* p)
 {
-    return __ldcg(&p->own);
+    return __ldcg(p);
 }
 
 // ---- label map + packed colours -> pixel words ----------------------------------------------------------------------
-__global__ void __launch_bounds__(256) wsp_pack(const int32_t* __restrict__ m, const uint32_t* __restrict__ pix, WspPx* __restrict__ px, size_t n)
+__global__ void __launch_bounds__(256) wsp_pack(const int32_t* __restrict__ m, WspPx* __restrict__ px, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    WspPx v;
-    v.own = ((unsigned long long)WSP_COMMITTED << 32) | (unsigned)m[i];
-    v.pix = pix[i];
-    v.pad = 0;
-    px[i] = v;
+    if (i < n) px[i] = ((unsigned long long)WSP_COMMITTED << 32) | (unsigned)m[i];
 }
 
 __global__ void __launch_bounds__(256) wsp_unpack(const WspPx* __restrict__ px, int32_t* __restrict__ m, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) m[i] = (int)(unsigned)px[i].own;
+    if (i < n) m[i] = (int)(unsigned)px[i];
 }
 
 // ---- candidates: unlabelled 4-neighbours of a seed, keyed (level, row-major position) = OpenCV's initial push order --
@@ -160,7 +152,7 @@ __global__ void __launch_bounds__(256) wsp_candidates(const int32_t* __restrict_
 __global__ void __launch_bounds__(256) wsp_mark_queued(WspPx* __restrict__ px, const int* __restrict__ vals, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) px[vals[i]].own = ((unsigned long long)WSP_COMMITTED << 32) | (unsigned)WS_IN_QUEUE;
+    if (i < n) px[vals[i]] = ((unsigned long long)WSP_COMMITTED << 32) | (unsigned)WS_IN_QUEUE;
 }
 
 // start[l] = first sorted key whose level (top byte) is >= l, l = 0..256
@@ -275,9 +267,10 @@ __global__ void __launch_bounds__(128) wsp_run(WspArgs a)
             if (p.link_old[d] != link_exp) bad = true;  // the tail we linked it behind had been taken by a lower rank
         }
         WspRec* R = a.rec + p.ri;
-        *reinterpret_cast<int4*>(&R->pixel) = make_int4(p.x, q, p.seq, p.lab);
-        *reinterpret_cast<int4*>(R->view) = make_int4(p.vis[0], p.vis[1], p.vis[2], p.vis[3]);
-        *reinterpret_cast<uint2*>(R->lvl) = make_uint2(p.lv, pm | p.self);
+        // streaming stores: the record pool must not push the claim words out of L2
+        __stcs(reinterpret_cast<int4*>(&R->pixel), make_int4(p.x, q, p.seq, p.lab));
+        __stcs(reinterpret_cast<int4*>(R->view), make_int4(p.vis[0], p.vis[1], p.vis[2], p.vis[3]));
+        __stcs(reinterpret_cast<uint2*>(R->lvl), make_uint2(p.lv, pm | p.self));
         if (bad) void_run = true;
     };
     unsigned long long ri = (unsigned long long)q;  // record of the pop being processed (the entry's record is slot q)
@@ -289,17 +282,19 @@ __global__ void __launch_bounds__(128) wsp_run(WspArgs a)
             chunk_left = n;
         }
         const int off[4] = {-1, 1, -ms, ms};
-        const uint4 wx4 = __ldcg(reinterpret_cast<const uint4*>(px + x));
-        uint4 wn[4];
+        const unsigned long long wx = __ldcg(px + x);
+        unsigned long long wn[4];
+        uint32_t cn[4];
 #pragma unroll
-        for (int d = 0; d < 4; d++) wn[d] = __ldcg(reinterpret_cast<const uint4*>(px + x + off[d]));
+        for (int d = 0; d < 4; d++) wn[d] = __ldcg(px + x + off[d]);
+        const uint32_t cx = __ldg(a.pix + x);
+#pragma unroll
+        for (int d = 0; d < 4; d++) cn[d] = __ldg(a.pix + x + off[d]);
         const int stolen = x != e ? *dflag : 0;
         settle();  // the previous pop, while these loads are in flight
-        const unsigned long long wx = ((unsigned long long)wx4.y << 32) | wx4.x;
-        const uint32_t cx = wx4.z;
         if (x != e) {
             // x must still be ours, queued in our sub-flood; its word carries the link to its successor
-            const bool ours = wx4.y == mytag && wsp_state(wx) <= WSP_PRIVATE;
+            const bool ours = wsp_tag(wx) == mytag && wsp_state(wx) <= WSP_PRIVATE;
             if (chunk + chunk_left > a.rec_cap) {
                 a.ctl->overflow = 1;
                 chunk_left = 0;
@@ -317,9 +312,8 @@ __global__ void __launch_bounds__(128) wsp_run(WspArgs a)
         unsigned self = 0;
 #pragma unroll
         for (int d = 0; d < 4; d++) {
-            const unsigned long long w = ((unsigned long long)wn[d].y << 32) | wn[d].x;
-            vis[d] = wsp_visible(w, uq + 1);
-            if (wn[d].y != WSP_COMMITTED && (wn[d].y >> 1) == uq) self |= 16u << d;
+            vis[d] = wsp_visible(wn[d], uq + 1);
+            if (wsp_tag(wn[d]) != WSP_COMMITTED && (wsp_tag(wn[d]) >> 1) == uq) self |= 16u << d;
         }
         int lab = 0;
 #pragma unroll
@@ -341,21 +335,21 @@ __global__ void __launch_bounds__(128) wsp_run(WspArgs a)
 #pragma unroll
         for (int d = 0; d < 4; d++) p.vis[d] = vis[d];
         p.cas_exp = p.cas_old = wx;
-        if (x == e) px[x].own = wsp_word(mytag | 1u, lab);  // nobody else ever claims a queued entry
-        else p.cas_old = atomicCAS(&px[x].own, wx, wsp_word(mytag, lab));
+        if (x == e) px[x] = wsp_word(mytag | 1u, lab);  // nobody else ever claims a queued entry
+        else p.cas_old = atomicCAS(&px[x], wx, wsp_word(mytag, lab));
         if (lab != WS_WSHED) {
 #pragma unroll
             for (int d = 0; d < 4; d++) {
                 p.link_old[d] = link_exp;
                 if (vis[d] != 0) continue;
                 const int y = x + off[d];
-                const int l = wsp_diff(cx, wn[d].z);
-                p.old[d] = atomicMin(&px[y].own, wsp_word(mytag, l < c ? WSP_PRIVATE - WSP_NOLINK : WS_IN_QUEUE));
+                const int l = wsp_diff(cx, cn[d]);
+                p.old[d] = atomicMin(&px[y], wsp_word(mytag, l < c ? WSP_PRIVATE - WSP_NOLINK : WS_IN_QUEUE));
                 p.att |= 1u << d;
                 p.lv |= (unsigned)l << (8 * d);
                 if (l < c) {  // into our queue, as if the claim had succeeded (settle() checks)
                     if (mask[l >> 5] & (1u << (l & 31))) {
-                        p.link_old[d] = atomicCAS(&px[tail[l]].own, link_exp, wsp_word(mytag, WSP_PRIVATE - y));
+                        p.link_old[d] = atomicCAS(&px[tail[l]], link_exp, wsp_word(mytag, WSP_PRIVATE - y));
                         tail[l] = y;
                     } else {
                         mask[l >> 5] |= 1u << (l & 31);
@@ -470,7 +464,7 @@ __device__ __forceinline__ void wsp_retract_one(const WspArgs& a, unsigned long 
     auto release = [&](WspPx* p) {  // only what is (still) ours goes back to the committed state it replaced
         const unsigned long long v = wsp_ld_own(p);
         const unsigned t = wsp_tag(v);
-        if (t != WSP_COMMITTED && (t >> 1) == q) atomicCAS(&p->own, v, wsp_word(WSP_COMMITTED, wsp_under(t)));
+        if (t != WSP_COMMITTED && (t >> 1) == q) atomicCAS(p, v, wsp_word(WSP_COMMITTED, wsp_under(t)));
     };
     release(a.px + x);
 #pragma unroll
@@ -494,7 +488,7 @@ __device__ __forceinline__ void wsp_commit_one(const WspArgs& a, unsigned long l
     const unsigned q = (unsigned)R->rank;
     const int ms = a.ms;
     const int off[4] = {-1, 1, -ms, ms};
-    a.px[x].own = wsp_word(WSP_COMMITTED, R->label);
+    a.px[x] = wsp_word(WSP_COMMITTED, R->label);
     const unsigned pm = R->pushmask;
     const unsigned lv = *reinterpret_cast<const unsigned*>(R->lvl);
     const unsigned seq = (unsigned)R->popseq;
@@ -504,7 +498,7 @@ __device__ __forceinline__ void wsp_commit_one(const WspArgs& a, unsigned long l
         const int y = x + off[d];
         const int l = (int)((lv >> (8 * d)) & 0xff);
         if (l >= a.c) {  // stays queued after this round (a pixel queued below c was popped by a record of its own)
-            a.px[y].own = wsp_word(WSP_COMMITTED, WS_IN_QUEUE);
+            a.px[y] = wsp_word(WSP_COMMITTED, WS_IN_QUEUE);
             const unsigned k = atomicAdd(nkeys, 1u);
             keys[k] = ((unsigned long long)l << 56) | ((unsigned long long)q << 29) | ((unsigned long long)seq << 2) | (unsigned)d;
             vals[k] = y;
@@ -573,7 +567,7 @@ int ofxcv_wsp_flood(ofxcv_ctx* ctx, cudaStream_t s, int32_t* m, ptrdiff_t pitch,
     constexpr int MAX_GATHER = 32768 / (int)sizeof(WspSeg);
 
     OFXCV_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(WspCtl), s));
-    wsp_pack<<<(unsigned)((st + 255) / 256), 256, 0, s>>>(m, pix, px, st);
+    wsp_pack<<<(unsigned)((st + 255) / 256), 256, 0, s>>>(m, px, st);
     OFXCV_LAUNCH_CHECK(ctx);
     auto readback = [&](size_t bytes) -> int {
         OFXCV_CUDA(ctx, cudaMemcpyAsync(hctl, ctl, bytes, cudaMemcpyDeviceToHost, s));
@@ -619,6 +613,7 @@ int ofxcv_wsp_flood(ofxcv_ctx* ctx, cudaStream_t s, int32_t* m, ptrdiff_t pitch,
 
     WspArgs a;
     a.px = px;
+    a.pix = pix;
     a.rec = rec;
     a.dirty = dirty;
     a.runf = runf;

@@ -70,3 +70,42 @@ def test_watershed_1080p_1000_seeds(ctx, oracle, synth):
     got = ctx.watershed(img, mk)
     ref, pops = oracle.watershed(img, mk)
     assert np.array_equal(got, ref) and ctx.watershed_stats()["pops"] == pops
+
+
+def _image_classes(h, w, seed):
+    rng = np.random.default_rng(seed)
+    yield "noise", rng.integers(0, 256, (h, w, 3), dtype=np.uint8)            # levels spread over 0..255: phases above 32
+    yield "flat", np.full((h, w, 3), 77, np.uint8)                             # one phase, pure BFS generations
+    g = np.zeros((h, w, 3), np.uint8)
+    g[..., 0] = (np.arange(w) % 256)[None, :]
+    g[..., 1] = (np.arange(h) % 256)[:, None]
+    yield "gradient", g                                                        # level 1 everywhere, 255 at the wrap lines
+    b = rng.integers(0, 256, (h // 16 + 1, w // 16 + 1, 3), dtype=np.uint8)
+    yield "blocks", np.ascontiguousarray(np.kron(b, np.ones((16, 16, 1), np.uint8))[:h, :w])   # big sub-floods
+
+
+@pytest.mark.parametrize("mode", ["par", "seq"])
+def test_watershed_both_floods_on_image_classes(ctx, oracle, synth, monkeypatch, mode):
+    """The exact intra-frame parallel flood (watershed_par.cu: what one frame uses) and the one-thread flood (what a
+    long clip uses) both give the oracle's label map and pop count on every image class, whatever the scheduling."""
+    monkeypatch.setenv("OFXCV_WS_MODE", mode)
+    h, w = 270, 480
+    mk = synth.seed_markers(h, w, 40, 5)
+    for name, img in _image_classes(h, w, 7):
+        ref, pops = oracle.watershed(img, mk)
+        for rep in range(2 if mode == "par" else 1):      # the parallel flood converges to the same fixed point every time
+            got = ctx.watershed(img, mk)
+            assert np.array_equal(got, ref), (mode, name)
+            st = ctx.watershed_stats()
+            assert st["pops"] == pops, (mode, name, st)
+
+
+def test_watershed_parallel_flood_is_the_single_frame_path(ctx, synth):
+    """One frame goes through the round-synchronous parallel flood (rounds > 0 in the statistics), not the one-thread kernel."""
+    h, w = 240, 320
+    ctx.watershed(synth.texture(h, w, 3), synth.seed_markers(h, w, 12, 4))
+    import ctypes as C
+    s = (C.c_int64 * 4)()
+    import importlib
+    importlib.import_module("openfx-opencv_b200").lib().ofxcv_watershed_last_stats(ctx.h, s)
+    assert s[2] > 0 and s[3] >= s[2]
