@@ -36,6 +36,8 @@ typedef struct ofxcv_ctx ofxcv_ctx;
 typedef void* ofxcv_stream; /* cudaStream_t */
 
 typedef enum ofxcv_status {
+    OFXCV_ABORTED = 1,        /* the abort callback fired: the output is incomplete (maps to kOfxStatOK after a sync, like the
+                                 reference's `if (abort()) return;`) */
     OFXCV_OK = 0,
     OFXCV_ERR_BAD_ARG = -1,   /* NULL pointer, non-positive size, unsupported channel count ... */
     OFXCV_ERR_NO_DEVICE = -2, /* no CUDA device / context creation failed */
@@ -81,6 +83,27 @@ OFXCV_API int ofxcv_upload(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, const 
 OFXCV_API int ofxcv_download(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_host, const void* src_dev, size_t bytes);
 OFXCV_API int ofxcv_device_copy(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, const void* src_dev, size_t bytes);
 OFXCV_API int ofxcv_memset(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, int value, size_t bytes);
+
+/* the calling thread's current CUDA device (-1 on error) and the device that owns a device pointer (-1: host memory or
+ * unknown) -- what the OFX glue needs to pick a context of the right GPU when a host hands it device images
+ * (kOfxImageEffectPropCudaEnabled, ofxImageEffect.h:1013-1049). */
+OFXCV_API int ofxcv_current_device(void);
+OFXCV_API int ofxcv_pointer_device(const void* p);
+/* Rows of a (pageable) host image -> tight device rows (pitch = row_bytes) and back, the staging of an OFX host-memory clip
+ * (src_stride / dst_stride may be negative: ofxImageEffect.h:909-921).  Large images move in row chunks: worker threads
+ * copy between the caller's rows and the context's pinned staging while the DMA of the finished chunks runs.
+ * ofxcv_upload_rows returns once the caller's rows have been read (the DMA may still run on `stream`);
+ * ofxcv_download_rows returns once the caller's rows are written. */
+OFXCV_API int ofxcv_upload_rows(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, const void* src_host, ptrdiff_t src_stride,
+                                size_t row_bytes, int rows);
+OFXCV_API int ofxcv_download_rows(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_host, ptrdiff_t dst_stride, const void* src_dev,
+                                  size_t row_bytes, int rows);
+/* bytes moved host->device / device->host by the staging helpers of this library since it was loaded (all contexts) */
+OFXCV_API void ofxcv_transfer_stats(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* abort polling (the host's OfxImageEffectSuiteV1::abort, /root/reference/openfx/include/ofxImageEffect.h): when set, the
+ * flow entry points call cb(user) between pyramid scales and between the pairs / frames of a clip and stop enqueueing
+ * work once it returns non-zero; they then return OFXCV_ABORTED (> 0).  NULL clears it. */
+OFXCV_API void ofxcv_set_abort_callback(ofxcv_ctx* ctx, int (*cb)(void*), void* user);
 
 /* ---- dense optical flow ----------------------------------------------------------------------------- */
 /* Replaces cv::calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, iters, poly_n,

@@ -101,6 +101,12 @@ def lib():
         "ofxcv_download": (i, [vp, vp, vp, vp, sz]),
         "ofxcv_device_copy": (i, [vp, vp, vp, vp, sz]),
         "ofxcv_memset": (i, [vp, vp, vp, i, sz]),
+        "ofxcv_current_device": (i, []),
+        "ofxcv_pointer_device": (i, [vp]),
+        "ofxcv_upload_rows": (i, [vp, vp, vp, vp, pd, sz, i]),
+        "ofxcv_download_rows": (i, [vp, vp, vp, pd, vp, sz, i]),
+        "ofxcv_transfer_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "ofxcv_set_abort_callback": (None, [vp, vp, vp]),
         "ofxcv_fb_default_params": (None, [fbp]),
         "ofxcv_farneback_scales": (i, [i, i, fbp]),
         "ofxcv_farneback_algorithmic_bytes": (d, [i, i, fbp]),
@@ -254,6 +260,21 @@ class Context:
 
     def stream(self):
         return lib().ofxcv_ctx_stream(self.h)
+
+    def set_abort_callback(self, fn):
+        """fn() -> truthy aborts the flow calls of this context between pyramid scales / pairs (None clears it)."""
+        if fn is None:
+            self._abort_cb = None
+            lib().ofxcv_set_abort_callback(self.h, None, None)
+            return
+        self._abort_cb = C.CFUNCTYPE(C.c_int, C.c_void_p)(lambda _u: 1 if fn() else 0)
+        lib().ofxcv_set_abort_callback(self.h, C.cast(self._abort_cb, C.c_void_p), None)
+
+    def upload_rows(self, dst_d, arr2d_bytes_view, row_bytes, rows, src_stride):
+        self._check(lib().ofxcv_upload_rows(self.h, None, dst_d, arr2d_bytes_view, src_stride, row_bytes, rows), "ofxcv_upload_rows")
+
+    def download_rows(self, dst_ptr, dst_stride, src_d, row_bytes, rows):
+        self._check(lib().ofxcv_download_rows(self.h, None, dst_ptr, dst_stride, src_d, row_bytes, rows), "ofxcv_download_rows")
 
     def launch_count(self):
         return int(lib().ofxcv_launch_count(self.h))
@@ -553,6 +574,14 @@ class Context:
         r, l, o = self.to_device(rgb), self.to_device(labels), self.alloc(w * h * 4)
         self._check(lib().ofxcv_labels_to_rgba8(self.h, None, r.ptr, w * 3, l.ptr, w * 4, o.ptr, w * 4, w, h, int(nlabels)), "ofxcv_labels_to_rgba8")
         return o.download((h, w, 4), np.uint8)
+
+
+def transfer_stats(library=None):
+    """(host->device bytes, device->host bytes) moved by the staging helpers of a loaded libofxcv_b200.so so far."""
+    L = library or lib()
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    L.ofxcv_transfer_stats(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
 
 
 def farneback_algorithmic_bytes(w, h, params=None):

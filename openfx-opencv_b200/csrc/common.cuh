@@ -70,6 +70,10 @@ struct ofxcv_ctx {
     int ip_fill_blocks_per_sm = 8;  // persistent CTAs of the inpaint fill kernel per SM (ofxcv_inpaint_set_fill_blocks)
     cudaEvent_t tv_ev[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t tv_ctrl_off = 0;  // where the last ofxcv_tvl1_u8 put its control block inside WS_TV_ARENA
+    std::vector<cudaEvent_t> xfer_ev;     // chunk events of ofxcv_download_rows
+    cudaEvent_t xfer_up_done = nullptr;   // the last DMA out of the upload staging buffer
+    int (*abort_cb)(void*) = nullptr;     // polled between pyramid scales / pairs / frames (ofxcv_set_abort_callback)
+    void* abort_user = nullptr;
     int64_t inpaint_stats[4] = {0, 0, 0, 0};
     int64_t watershed_stats[4] = {0, 0, 0, 0};  // [0] pops (-1 = still on the device), [1] frames, [2] rounds, [3] passes of the parallel flood
     std::vector<int> watershed_seq_frames;  // frames of the last call that ran on the one-thread flood
@@ -148,6 +152,7 @@ static inline bool ofxcv_is_pinned(const void* p)
 }
 
 static inline int ofxcv_div_up(int a, int b) { return (a + b - 1) / b; }
+static inline bool ofxcv_aborted(const ofxcv_ctx* ctx) { return ctx->abort_cb && ctx->abort_cb(ctx->abort_user) != 0; }
 
 // watershed_par.cu: exact intra-frame parallel flood of one prepared frame (see the header of that file); returns 1 when
 // the flood is degenerate and the one-thread kernel of watershed.cu should run instead (label map restored)

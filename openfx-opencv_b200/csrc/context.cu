@@ -1,5 +1,30 @@
 // Context, memory and timing plumbing of the C ABI (include/ofxcv_abi.h).  No image arithmetic here.
+#include <atomic>
+#include <thread>
+
 #include "common.cuh"
+
+static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
+
+namespace {
+int xfer_workers()
+{
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc >= 8 ? 4 : hc >= 4 ? 2 : 1;
+}
+// runs work() on up to n threads; a thread that cannot be created is replaced by the calling thread doing the work
+template <class F>
+void run_workers(int n, F&& work, std::vector<std::thread>& th)
+{
+    for (int t = 0; t < n; t++) {
+        try {
+            th.emplace_back(work);
+        } catch (...) {
+            break;  // EAGAIN etc.: whoever is running (or the caller, in join_workers) picks the chunks up
+        }
+    }
+}
+}  // namespace
 
 int ofxcv_fail(ofxcv_ctx* ctx, cudaError_t e, const char* what)
 {
@@ -82,6 +107,7 @@ const char* ofxcv_status_string(int status)
 {
     switch (status) {
         case OFXCV_OK: return "ok";
+        case OFXCV_ABORTED: return "aborted by the host";
         case OFXCV_ERR_BAD_ARG: return "bad argument";
         case OFXCV_ERR_NO_DEVICE: return "no CUDA device";
         case OFXCV_ERR_MEMORY: return "out of device or pinned memory";
@@ -151,6 +177,8 @@ void ofxcv_destroy(ofxcv_ctx* ctx)
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->seq_ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->xfer_ev) cudaEventDestroy(e);
+    if (ctx->xfer_up_done) cudaEventDestroy(ctx->xfer_up_done);
     for (int f = 0; f < 3; f++)
         for (auto& t : ctx->timed[f]) {
             cudaEventDestroy(t.a);
@@ -321,6 +349,7 @@ int ofxcv_upload(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, const void* src_
     if (!dst_dev || !src_host) return OFXCV_ERR_BAD_ARG;
     ofxcv_device_guard g(ctx->device);
     OFXCV_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, pick(ctx, s)));
+    g_h2d_bytes += bytes;
     return OFXCV_OK;
 }
 
@@ -330,6 +359,7 @@ int ofxcv_download(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_host, const void* s
     if (!dst_host || !src_dev) return OFXCV_ERR_BAD_ARG;
     ofxcv_device_guard g(ctx->device);
     OFXCV_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, pick(ctx, s)));
+    g_d2h_bytes += bytes;
     return OFXCV_OK;
 }
 
@@ -348,6 +378,158 @@ int ofxcv_memset(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, int value, size_
     if (!dst_dev) return OFXCV_ERR_BAD_ARG;
     ofxcv_device_guard g(ctx->device);
     OFXCV_CUDA(ctx, cudaMemsetAsync(dst_dev, value, bytes, pick(ctx, s)));
+    return OFXCV_OK;
+}
+
+int ofxcv_current_device(void)
+{
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return d;
+}
+
+int ofxcv_pointer_device(const void* p)
+{
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+
+void ofxcv_set_abort_callback(ofxcv_ctx* ctx, int (*cb)(void*), void* user)
+{
+    if (!ctx) return;
+    ctx->abort_cb = cb;
+    ctx->abort_user = user;
+}
+
+void ofxcv_transfer_stats(uint64_t* h2d_bytes, uint64_t* d2h_bytes)
+{
+    if (h2d_bytes) *h2d_bytes = g_h2d_bytes.load();
+    if (d2h_bytes) *d2h_bytes = g_d2h_bytes.load();
+}
+
+// rows of a host image <-> tight device rows.  Large images are cut into row chunks: a few workers copy chunks between the
+// caller's (pageable) rows and the context's pinned staging while the DMA of the chunks that are ready already runs.
+
+int ofxcv_upload_rows(ofxcv_ctx* ctx, ofxcv_stream s_, void* dst_dev, const void* src_host, ptrdiff_t src_stride, size_t row_bytes, int rows)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!dst_dev || !src_host || rows <= 0 || row_bytes == 0) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard g(ctx->device);
+    cudaStream_t s = pick(ctx, s_);
+    const size_t total = row_bytes * (size_t)rows;
+    if (src_stride == (ptrdiff_t)row_bytes && ofxcv_is_pinned(src_host)) {  // page-locked and dense: straight over PCIe
+        OFXCV_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, total, cudaMemcpyHostToDevice, s));
+        g_h2d_bytes += total;
+        return OFXCV_OK;
+    }
+    char* pinned = (char*)ofxcv_pin(ctx, 2, total);
+    if (!pinned) return OFXCV_ERR_MEMORY;
+    if (!ctx->xfer_up_done) OFXCV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->xfer_up_done, cudaEventDisableTiming));
+    else OFXCV_CUDA(ctx, cudaEventSynchronize(ctx->xfer_up_done));  // the previous DMA out of the staging buffer has finished
+    const int nch = rows >= 256 && total >= ((size_t)8 << 20) ? 16 : 1;
+    const char* src = (const char*)src_host;
+    auto rows_of = [&](int k, int& y0, int& y1) {
+        y0 = (int)((long long)rows * k / nch);
+        y1 = (int)((long long)rows * (k + 1) / nch);
+    };
+    std::vector<std::atomic<int>> done(nch);
+    for (auto& d : done) d.store(0, std::memory_order_relaxed);
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= nch) return;
+            int y0, y1;
+            rows_of(k, y0, y1);
+            for (int y = y0; y < y1; y++) memcpy(pinned + (size_t)y * row_bytes, src + (ptrdiff_t)y * src_stride, row_bytes);
+            done[k].store(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> th;
+    if (nch > 1) run_workers(xfer_workers(), work, th);
+    if (th.empty()) work();
+    cudaError_t err = cudaSuccess;
+    for (int k = 0; k < nch; k++) {
+        while (!done[k].load(std::memory_order_acquire)) {
+            if (th.empty()) break;
+            std::this_thread::yield();
+        }
+        int y0, y1;
+        rows_of(k, y0, y1);
+        if (err == cudaSuccess)
+            err = cudaMemcpyAsync((char*)dst_dev + (size_t)y0 * row_bytes, pinned + (size_t)y0 * row_bytes, (size_t)(y1 - y0) * row_bytes,
+                                  cudaMemcpyHostToDevice, s);
+    }
+    for (auto& t : th) t.join();
+    if (err != cudaSuccess) return ofxcv_fail(ctx, err, "cudaMemcpyAsync(upload rows)");
+    OFXCV_CUDA(ctx, cudaEventRecord(ctx->xfer_up_done, s));
+    g_h2d_bytes += total;
+    return OFXCV_OK;
+}
+
+int ofxcv_download_rows(ofxcv_ctx* ctx, ofxcv_stream s_, void* dst_host, ptrdiff_t dst_stride, const void* src_dev, size_t row_bytes, int rows)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    if (!dst_host || !src_dev || rows <= 0 || row_bytes == 0) return OFXCV_ERR_BAD_ARG;
+    ofxcv_device_guard g(ctx->device);
+    cudaStream_t s = pick(ctx, s_);
+    const size_t total = row_bytes * (size_t)rows;
+    if (dst_stride == (ptrdiff_t)row_bytes && ofxcv_is_pinned(dst_host)) {
+        OFXCV_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, total, cudaMemcpyDeviceToHost, s));
+        OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+        g_d2h_bytes += total;
+        return OFXCV_OK;
+    }
+    char* pinned = (char*)ofxcv_pin(ctx, 3, total);
+    if (!pinned) return OFXCV_ERR_MEMORY;
+    const int nch = rows >= 256 && total >= ((size_t)8 << 20) ? 16 : 1;
+    while ((int)ctx->xfer_ev.size() < nch) {
+        cudaEvent_t e;
+        OFXCV_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->xfer_ev.push_back(e);
+    }
+    auto rows_of = [&](int k, int& y0, int& y1) {
+        y0 = (int)((long long)rows * k / nch);
+        y1 = (int)((long long)rows * (k + 1) / nch);
+    };
+    for (int k = 0; k < nch; k++) {  // the whole download is enqueued first; the workers follow the chunks as they land
+        int y0, y1;
+        rows_of(k, y0, y1);
+        OFXCV_CUDA(ctx, cudaMemcpyAsync(pinned + (size_t)y0 * row_bytes, (const char*)src_dev + (size_t)y0 * row_bytes,
+                                        (size_t)(y1 - y0) * row_bytes, cudaMemcpyDeviceToHost, s));
+        OFXCV_CUDA(ctx, cudaEventRecord(ctx->xfer_ev[k], s));
+    }
+    char* dst = (char*)dst_host;
+    std::atomic<int> next{0};
+    std::atomic<int> failed{0};
+    const int device = ctx->device;
+    auto work = [&]() {
+        cudaSetDevice(device);
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= nch) return;
+            if (cudaEventSynchronize(ctx->xfer_ev[k]) != cudaSuccess) {
+                failed.store(1);
+                return;
+            }
+            int y0, y1;
+            rows_of(k, y0, y1);
+            for (int y = y0; y < y1; y++) memcpy(dst + (ptrdiff_t)y * dst_stride, pinned + (size_t)y * row_bytes, row_bytes);
+        }
+    };
+    std::vector<std::thread> th;
+    if (nch > 1) run_workers(xfer_workers() - 1, work, th);
+    work();  // the calling thread takes its share (and everything, should no thread have started)
+    for (auto& t : th) t.join();
+    if (failed.load()) return ofxcv_fail(ctx, cudaGetLastError(), "cudaEventSynchronize(download rows)");
+    g_d2h_bytes += total;
     return OFXCV_OK;
 }
 

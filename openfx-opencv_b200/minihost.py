@@ -45,6 +45,8 @@ def lib():
         L.mh_clip_prop_string.restype = s; L.mh_clip_prop_string.argtypes = [vp, s, s, i]
         L.mh_set_clip_image.restype = i; L.mh_set_clip_image.argtypes = [vp, s, d, vp, i, i, i, s, s, i, i]
         L.mh_clear_clip_images.restype = i; L.mh_clear_clip_images.argtypes = [vp, s]
+        L.mh_set_image_props.restype = i; L.mh_set_image_props.argtypes = [vp, s, d, d, d, s]
+        L.mh_provide_unique_identifiers.restype = None; L.mh_provide_unique_identifiers.argtypes = [i]
         L.mh_render.restype = i; L.mh_render.argtypes = [vp, d, i, i, i, i, d, d, i]
         L.mh_frames_needed.restype = i; L.mh_frames_needed.argtypes = [vp, d, s, C.POINTER(d)]
         L.mh_instance_changed.restype = i; L.mh_instance_changed.argtypes = [vp, s]
@@ -152,6 +154,17 @@ class Plugin:
         st = lib().mh_set_clip_image(self.h, clip.encode(), float(time), C.c_void_p(dptr), w, h, w * c * np.dtype(dtype).itemsize,
                                      depth.encode(), comps.encode(), x1, y1)
         assert st == 0, st
+
+    def set_image_props(self, clip, time, scale=(1.0, 1.0), field="OfxFieldNone"):
+        """What the host writes on an already set image: its render scale and field (a mismatch with the render arguments
+        must fail the render: VectorGenerator.cpp:531-536)."""
+        st = lib().mh_set_image_props(self.h, clip.encode(), float(time), float(scale[0]), float(scale[1]), field.encode())
+        assert st == 0, st
+
+    @staticmethod
+    def provide_unique_identifiers(on):
+        """Hosts that do not set kOfxImagePropUniqueIdentifier (the staged-frame cache of the plugin must then stay off)."""
+        lib().mh_provide_unique_identifiers(1 if on else 0)
 
     def clear_images(self, clip):
         lib().mh_clear_clip_images(self.h, clip.encode())

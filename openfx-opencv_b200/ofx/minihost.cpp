@@ -204,7 +204,12 @@ struct ImageDesc {
     int w, h, rowBytes;
     std::string depth, comps;
     int x1, y1;
+    std::string uid;                // kOfxImagePropUniqueIdentifier: changes whenever the host replaces the image ("" = not provided)
+    double sx = 1, sy = 1;          // kOfxImageEffectPropRenderScale of the image
+    std::string field = "OfxFieldNone";
 };
+long gImageSerial = 0;
+bool gProvideUid = true;
 struct Clip {
     std::string name;
     PropSet props;
@@ -263,9 +268,10 @@ OfxStatus clipGetImage(OfxImageClipHandle ch, OfxTime t, const OfxRectD*, OfxPro
     propSetInt(p, kOfxImagePropRowBytes, 0, d.rowBytes);
     propSetString(p, kOfxImageEffectPropPixelDepth, 0, d.depth.c_str());
     propSetString(p, kOfxImageEffectPropComponents, 0, d.comps.c_str());
-    double one[2] = {1, 1};
-    propSetDoubleN(p, kOfxImageEffectPropRenderScale, 2, one);
-    propSetString(p, "OfxImagePropField", 0, "OfxFieldNone");
+    double sc[2] = {d.sx, d.sy};
+    propSetDoubleN(p, kOfxImageEffectPropRenderScale, 2, sc);
+    propSetString(p, "OfxImagePropField", 0, d.field.c_str());
+    if (gProvideUid && !d.uid.empty()) propSetString(p, "OfxImagePropUniqueIdentifier", 0, d.uid.c_str());
     c->outstanding++;
     if (gCurrent) gCurrent->images_fetched++;
     *out = p;
@@ -457,10 +463,26 @@ MH int mh_set_clip_image(void* h, const char* clip, double time, void* data, int
     if (!L->instance) return kOfxStatErrBadHandle;
     auto it = L->instance->clips.find(clip);
     if (it == L->instance->clips.end()) return kOfxStatErrUnknown;
-    it->second->images[lround(time * 1000)] = ImageDesc{data, w, hgt, rowBytes, depth, comps, x1, y1};
+    ImageDesc desc{data, w, hgt, rowBytes, depth, comps, x1, y1};
+    desc.uid = std::string(clip) + ":" + std::to_string(lround(time * 1000)) + ":" + std::to_string(++gImageSerial);
+    it->second->images[lround(time * 1000)] = desc;
     propSetInt((OfxPropertySetHandle)&it->second->props, kOfxImageClipPropConnected, 0, 1);
     return kOfxStatOK;
 }
+// test hooks: what a (mis)behaving host may put on an image, and hosts that do not label their images
+MH int mh_set_image_props(void* h, const char* clip, double time, double sx, double sy, const char* field)
+{
+    Loaded* L = (Loaded*)h;
+    auto it = L->instance->clips.find(clip);
+    if (it == L->instance->clips.end()) return kOfxStatErrUnknown;
+    auto im = it->second->images.find(lround(time * 1000));
+    if (im == it->second->images.end()) return kOfxStatFailed;
+    im->second.sx = sx;
+    im->second.sy = sy;
+    if (field) im->second.field = field;
+    return kOfxStatOK;
+}
+MH void mh_provide_unique_identifiers(int on) { gProvideUid = on != 0; }
 MH int mh_clear_clip_images(void* h, const char* clip)
 {
     Loaded* L = (Loaded*)h;

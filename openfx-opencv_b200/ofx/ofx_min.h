@@ -2,7 +2,8 @@
  * ofx_min.h — the part of the OpenFX 1.4 image-effect C ABI these plugins use, restated from the public standard
  * so that the bundles build hermetically (the GPU box has no /root/reference).  Layout-identical to the headers the
  * reference compiles against (/root/reference/openfx/include/ofxCore.h:61-229,:550-598, ofxProperty.h:49-328,
- * ofxImageEffect.h:1145-1414, ofxParam.h:879-1250); tests/test_ofx_abi_layout.py compiles a translation unit that
+ * ofxImageEffect.h:1145-1414, ofxParam.h:879-1250); tests/test_ofx_plugins.py
+ * (test_ofx_min_header_layout_matches_reference) compiles a translation unit that
  * includes BOTH and static_asserts every struct size / member offset whenever the reference tree is present.
  */
 #ifndef OFX_MIN_H
@@ -158,6 +159,8 @@ typedef struct OfxParameterSuiteV1 {
 #define kOfxImageEffectContextGeneral "OfxImageEffectContextGeneral"
 #define kOfxImageEffectPropRenderWindow "OfxImageEffectPropRenderWindow"
 #define kOfxImageEffectPropRenderScale "OfxImageEffectPropRenderScale"
+#define kOfxImagePropUniqueIdentifier "OfxImagePropUniqueIdentifier"
+#define kOfxImagePropField "OfxImagePropField"
 #define kOfxImageEffectPropFieldToRender "OfxImageEffectPropFieldToRender"
 #define kOfxImageEffectPropFrameRange "OfxImageEffectPropFrameRange"
 #define kOfxImageEffectPropPixelDepth "OfxImageEffectPropPixelDepth"

@@ -7,12 +7,12 @@
 #include <stdint.h>
 #include <string.h>
 
-#include <atomic>
+#include <stdlib.h>
+
 #include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../../include/ofxcv_abi.h"
@@ -82,22 +82,30 @@ OfxStatus guarded(F&& f)
     }
 }
 
-// ---- contexts: one per concurrent render (FullySafe), created lazily on the calling thread's current device ----
+// ---- contexts: one per concurrent render (FullySafe), pooled PER DEVICE ------------------------------------------------
+// A context lives on one GPU (its stream, workspaces, cached pyramids).  The device of a render is OFXCV_DEVICE when set,
+// else the device that owns the host's device images (CUDA render), else the calling thread's current device; a pooled
+// context is only handed out again for the device it was created on.
 class ContextPool {
 public:
-    ofxcv_ctx* acquire()
+    static int default_device()
     {
+        if (const char* e = getenv("OFXCV_DEVICE")) return atoi(e);
+        return ofxcv_current_device();
+    }
+    ofxcv_ctx* acquire(int device)
+    {
+        if (device < 0) device = default_device();
         {
             std::lock_guard<std::mutex> l(m_);
-            if (!free_.empty()) {
-                ofxcv_ctx* c = free_.back();
-                free_.pop_back();
-                return c;
-            }
+            for (size_t i = free_.size(); i-- > 0;)
+                if (ofxcv_device(free_[i]) == device) {
+                    ofxcv_ctx* c = free_[i];
+                    free_.erase(free_.begin() + (ptrdiff_t)i);
+                    return c;
+                }
         }
-        int dev = -1;
-        if (const char* e = getenv("OFXCV_DEVICE")) dev = atoi(e);
-        ofxcv_ctx* c = ofxcv_create(dev);
+        ofxcv_ctx* c = ofxcv_create(device);
         if (!c) throw StatusException{kOfxStatErrMissingHostFeature};
         return c;
     }
@@ -120,8 +128,23 @@ private:
 struct ContextLease {
     ContextPool& pool;
     ofxcv_ctx* ctx;
-    explicit ContextLease(ContextPool& p) : pool(p), ctx(p.acquire()) {}
-    ~ContextLease() { pool.release(ctx); }
+    explicit ContextLease(ContextPool& p, int device = -1) : pool(p), ctx(p.acquire(device)) {}
+    ~ContextLease()
+    {
+        ofxcv_set_abort_callback(ctx, nullptr, nullptr);
+        pool.release(ctx);
+    }
+};
+// declared AFTER the image guards of a render that hands device pointers to the library: whatever way the action is left
+// (abort, a missing neighbour frame, an error), the context's queued work is finished before the host gets its images back
+struct SyncOnExit {
+    ofxcv_ctx* ctx;
+    explicit SyncOnExit(ofxcv_ctx* c) : ctx(c) {}
+    ~SyncOnExit()
+    {
+        if (ctx) ofxcv_synchronize(ctx);
+    }
+    SyncOnExit(const SyncOnExit&) = delete;
 };
 
 // ---- images --------------------------------------------------------------------------------------------
@@ -130,7 +153,8 @@ struct Image {
     char* data = nullptr;  // address of pixel (bounds.x1, bounds.y1); rows go UP with +rowBytes
     OfxRectI bounds{0, 0, 0, 0};
     int rowBytes = 0;
-    std::string depth, components;
+    std::string depth, components, uid, field;  // uid: kOfxImagePropUniqueIdentifier ("" when the host gives none)
+    OfxPointD scale{1, 1};
     int ncomp() const { return components == kOfxImageComponentRGBA ? 4 : components == kOfxImageComponentRGB ? 3 : 1; }
     int bytes_per_comp() const { return depth == kOfxBitDepthFloat ? 4 : depth == kOfxBitDepthShort ? 2 : 1; }
     char* row(int y) const { return data + (ptrdiff_t)(y - bounds.y1) * rowBytes; }
@@ -155,6 +179,11 @@ public:
         img.depth = s ? s : "";
         check(h.prop->propGetString(p, kOfxImageEffectPropComponents, 0, &s));
         img.components = s ? s : "";
+        s = nullptr;
+        if (h.prop->propGetString(p, kOfxImagePropUniqueIdentifier, 0, &s) == kOfxStatOK && s) img.uid = s;
+        s = nullptr;
+        if (h.prop->propGetString(p, kOfxImagePropField, 0, &s) == kOfxStatOK && s) img.field = s;
+        if (h.prop->propGetDoubleN(p, kOfxImageEffectPropRenderScale, 2, &img.scale.x) != kOfxStatOK) img.scale = {1, 1};
         img.data = (char*)d;
         if (!img.data) throw StatusException{kOfxStatFailed};
     }
@@ -174,6 +203,7 @@ struct RenderArgs {
     OfxRectI window{0, 0, 0, 0};
     OfxPointD scale{1, 1};
     int cudaEnabled = 0;
+    std::string field;
 };
 inline RenderArgs render_args(const Host& h, OfxPropertySetHandle inArgs)
 {
@@ -182,6 +212,8 @@ inline RenderArgs render_args(const Host& h, OfxPropertySetHandle inArgs)
     check(h.prop->propGetIntN(inArgs, kOfxImageEffectPropRenderWindow, 4, &a.window.x1));
     if (h.prop->propGetDoubleN(inArgs, kOfxImageEffectPropRenderScale, 2, &a.scale.x) != kOfxStatOK) a.scale = {1, 1};
     if (h.prop->propGetInt(inArgs, kOfxImageEffectPropCudaEnabled, 0, &a.cudaEnabled) != kOfxStatOK) a.cudaEnabled = 0;
+    char* f = nullptr;
+    if (h.prop->propGetString(inArgs, kOfxImageEffectPropFieldToRender, 0, &f) == kOfxStatOK && f) a.field = f;
     return a;
 }
 
@@ -295,74 +327,96 @@ inline bool window_inside(const OfxRectI& win, const OfxRectI& b)
     return win.x1 >= b.x1 && win.y1 >= b.y1 && win.x2 <= b.x2 && win.y2 <= b.y2 && win.x2 > win.x1 && win.y2 > win.y1;
 }
 
-// Large host images (a 4K float RGBA frame is 133 MB): one thread copying rows into the pinned staging buffer runs at
-// ~8 GB/s and would take three times as long as the PCIe transfer it feeds.  The window is cut into row chunks; a few
-// workers copy chunks into (out of) the pinned buffer while the calling thread enqueues the H2D copy of every chunk as
-// soon as it is complete, so the row copies and the DMA overlap.  `win` must lie inside the image bounds.
-inline int staging_workers()
+// host image window <-> tight device rows: the row-chunk pipeline lives behind the C ABI (ofxcv_upload_rows /
+// ofxcv_download_rows: worker threads + the context's pinned staging + chunk events); `win` must lie inside the bounds
+inline void upload_window(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, int bpp, void* dev)
 {
-    const unsigned hc = std::thread::hardware_concurrency();
-    return hc >= 8 ? 4 : hc >= 4 ? 2 : 1;
+    check_cv(ofxcv_upload_rows(ctx, nullptr, dev, img.pixel(win.x1, win.y1), img.rowBytes, (size_t)(win.x2 - win.x1) * bpp, win.y2 - win.y1));
 }
-inline void upload_window(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, int bpp, char* pinned, void* dev)
+inline void download_window(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, int bpp, const void* dev)
 {
-    const int w = win.x2 - win.x1, h = win.y2 - win.y1;
-    const size_t row = (size_t)w * bpp;
-    const int nch = h >= 256 && row * h >= (8u << 20) ? 16 : 1;
-    if (nch == 1) {
-        gather_rows(img, win, bpp, pinned);
-        check_cv(ofxcv_upload(ctx, nullptr, dev, pinned, row * h));
-        return;
-    }
-    std::vector<std::atomic<int>> done(nch);
-    for (auto& d : done) d.store(0, std::memory_order_relaxed);
-    std::atomic<int> next{0};
-    auto rows_of = [&](int k, int& y0, int& y1) {
-        y0 = (int)((long long)h * k / nch);
-        y1 = (int)((long long)h * (k + 1) / nch);
+    check_cv(ofxcv_download_rows(ctx, nullptr, img.pixel(win.x1, win.y1), img.rowBytes, dev, (size_t)(win.x2 - win.x1) * bpp, win.y2 - win.y1));
+}
+
+// ---- staged frames kept across renders -------------------------------------------------------------------------------
+// getFramesNeeded (VectorGenerator.cpp:675-695) makes render t+1 ask for two of the three frames render t staged.  A host
+// that labels its images (kOfxImagePropUniqueIdentifier: "changes whenever the image changes") lets us keep the staged
+// 8-bit gray frame + its content key on the device: the next render uploads and converts ONE new frame instead of three.
+class GrayCache {
+public:
+    struct Entry {
+        std::string uid;
+        OfxRectI win{0, 0, 0, 0};
+        int device = -1;
+        void* gray = nullptr;  // W*H bytes on `device` (owned)
+        size_t cap = 0;
+        uint64_t key = 0;      // ofxcv_content_key_u8 of the plane
+        uint64_t tick = 0;
+        int users = 0;
     };
-    auto work = [&]() {
-        for (;;) {
-            const int k = next.fetch_add(1);
-            if (k >= nch) return;
-            int y0, y1;
-            rows_of(k, y0, y1);
-            for (int y = y0; y < y1; y++)
-                memcpy(pinned + (size_t)y * row, img.row(win.y1 + y) + (ptrdiff_t)(win.x1 - img.bounds.x1) * bpp, row);
-            done[k].store(1, std::memory_order_release);
+    // a hit pins the entry (release() when the render is over); a miss returns nullptr
+    Entry* find(const std::string& uid, const OfxRectI& win, int device)
+    {
+        if (uid.empty()) return nullptr;
+        std::lock_guard<std::mutex> l(m_);
+        for (Entry& e : e_)
+            if (e.gray && e.device == device && e.uid == uid && !memcmp(&e.win, &win, sizeof(win))) {
+                e.tick = ++tick_;
+                e.users++;
+                hits_++;
+                return &e;
+            }
+        return nullptr;
+    }
+    // a pinned slot of at least `bytes` on the context's device for a frame that is about to be staged (nullptr: every
+    // slot is in use by concurrent renders -> the caller stages into its own scratch)
+    Entry* claim(ofxcv_ctx* ctx, const std::string& uid, const OfxRectI& win, size_t bytes)
+    {
+        if (uid.empty()) return nullptr;
+        std::lock_guard<std::mutex> l(m_);
+        Entry* v = nullptr;
+        for (Entry& e : e_)
+            if (e.users == 0 && (!v || e.tick < v->tick)) v = &e;
+        if (!v) return nullptr;
+        const int device = ofxcv_device(ctx);
+        if (v->gray && (v->device != device || v->cap < bytes)) {
+            ofxcv_device_free(ctx, v->gray);  // cudaFree synchronises: nobody is reading it (users == 0)
+            v->gray = nullptr;
         }
-    };
-    std::vector<std::thread> th;
-    for (int t = 0; t < staging_workers(); t++) th.emplace_back(work);
-    int st = OFXCV_OK;
-    for (int k = 0; k < nch; k++) {
-        while (!done[k].load(std::memory_order_acquire)) std::this_thread::yield();
-        int y0, y1;
-        rows_of(k, y0, y1);
-        if (st == OFXCV_OK) st = ofxcv_upload(ctx, nullptr, (char*)dev + (size_t)y0 * row, pinned + (size_t)y0 * row, (size_t)(y1 - y0) * row);
+        if (!v->gray) {
+            v->gray = ofxcv_device_alloc(ctx, bytes);
+            if (!v->gray) return nullptr;
+            v->cap = bytes;
+            v->device = device;
+        }
+        v->uid = uid;
+        v->win = win;
+        v->key = 0;
+        v->tick = ++tick_;
+        v->users = 1;
+        return v;
     }
-    for (auto& t : th) t.join();
-    check_cv(st);
-}
-// device (tight rows) -> host image window: one D2H copy, then the rows are scattered by the workers
-inline void download_window(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, int bpp, char* pinned, const void* dev)
-{
-    const int w = win.x2 - win.x1, h = win.y2 - win.y1;
-    const size_t row = (size_t)w * bpp;
-    check_cv(ofxcv_download(ctx, nullptr, pinned, dev, row * h));
-    check_cv(ofxcv_synchronize(ctx));
-    const int nt = h >= 256 && row * h >= (8u << 20) ? staging_workers() : 1;
-    if (nt == 1) {
-        scatter_rows(img, win, bpp, pinned);
-        return;
+    void release(Entry* e)
+    {
+        if (!e) return;
+        std::lock_guard<std::mutex> l(m_);
+        e->users--;
+        if (e->key == 0) e->uid.clear();  // staging did not complete: never match it
     }
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++)
-        th.emplace_back([&, t]() {
-            for (int y = (int)((long long)h * t / nt); y < (int)((long long)h * (t + 1) / nt); y++)
-                memcpy(img.row(win.y1 + y) + (ptrdiff_t)(win.x1 - img.bounds.x1) * bpp, pinned + (size_t)y * row, row);
-        });
-    for (auto& t : th) t.join();
-}
+    void clear(ofxcv_ctx* any_ctx_or_null)
+    {
+        std::lock_guard<std::mutex> l(m_);
+        for (Entry& e : e_) {
+            if (e.gray && any_ctx_or_null) ofxcv_device_free(any_ctx_or_null, e.gray);
+            e = Entry();
+        }
+    }
+    uint64_t hits() const { return hits_; }
+
+private:
+    std::mutex m_;
+    Entry e_[8];
+    uint64_t tick_ = 0, hits_ = 0;
+};
 
 }  // namespace ofxcv

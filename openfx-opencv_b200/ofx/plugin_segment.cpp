@@ -110,9 +110,8 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
     ContextLease lease(gPool);
     ofxcv_ctx* ctx = lease.ctx;
     const size_t n = (size_t)W * H;
-    PinBuf stage(ctx, 0, n * 4);
     DevBuf d_rgba(ctx, 0, n * 4), d_rgb(ctx, 1, n * 3), d_mask(ctx, 2, n), d_lab(ctx, 3, n * 4);
-    upload_window(ctx, src.img, win, 4, (char*)stage.p, d_rgba.p);
+    upload_window(ctx, src.img, win, 4, d_rgba.p);
     check_cv(ofxcv_rgba8_to_rgb8_mask(ctx, nullptr, (const uint8_t*)d_rgba.p, (ptrdiff_t)W * 4, (uint8_t*)d_rgb.p, (ptrdiff_t)W * 3,
                                       (uint8_t*)d_mask.p, W, W, H, 0));
     check_cv(ofxcv_seed_grid(ctx, nullptr, (int32_t*)d_lab.p, (ptrdiff_t)W * 4, W, H, gx, gy, 2));
@@ -121,7 +120,7 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
     check_cv(ofxcv_labels_to_rgba8(ctx, nullptr, (const uint8_t*)d_rgb.p, (ptrdiff_t)W * 3, (const int32_t*)d_lab.p, (ptrdiff_t)W * 4,
                                    (uint8_t*)d_rgba.p, (ptrdiff_t)W * 4, W, H, gx * gy));
     if (gHost.effect->abort(effect)) return kOfxStatOK;
-    download_window(ctx, dst.img, win, 4, (char*)stage.p, d_rgba.p);
+    download_window(ctx, dst.img, win, 4, d_rgba.p);
     return kOfxStatOK;
 }
 

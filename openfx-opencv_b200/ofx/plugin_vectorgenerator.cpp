@@ -21,6 +21,7 @@ using namespace ofxcv;
 namespace {
 Host gHost;
 ContextPool gPool;
+GrayCache gGray;
 
 struct Instance {
     OfxImageClipHandle src = nullptr, dst = nullptr;
@@ -147,45 +148,78 @@ void read_channels(Instance* d, OfxTime t, int ch[4], bool& fwd, bool& bwd)
     }
 }
 
-// one frame -> 8-bit sRGB gray on the device.  Host images: replicate-clamped gather of the render window into
-// pinned memory (= copyMakeBorder(BORDER_REPLICATE) to the union bounds, VectorGenerator.cpp:387-388), then H2D.
-void stage_gray(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, bool device_ptrs, PinBuf& stage, DevBuf& d_float, uint8_t* d_gray)
+// one frame -> 8-bit sRGB gray on the device.  Host images: the render window goes to the device through the row
+// pipeline of the C ABI (or, when it sticks out of the image bounds, is gathered replicate-clamped first =
+// copyMakeBorder(BORDER_REPLICATE) to the union bounds, VectorGenerator.cpp:387-388), then one conversion kernel.
+void stage_gray(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, bool device_ptrs, DevBuf& d_float, uint8_t* d_gray)
 {
     const int W = win.x2 - win.x1, H = win.y2 - win.y1, nc = img.ncomp();
     if (img.depth != kOfxBitDepthFloat) throw StatusException{kOfxStatErrImageFormat};
-    if (device_ptrs && window_inside(win, img.bounds)) {
+    if (device_ptrs) {
+        if (!window_inside(win, img.bounds)) throw StatusException{kOfxStatErrUnsupported};
+        // the host's device image must live on the GPU this context runs on (multi-GPU hosts render on several)
+        if (ofxcv_pointer_device(img.data) != ofxcv_device(ctx)) throw StatusException{kOfxStatErrUnsupported};
         check_cv(ofxcv_rgba32f_to_srgb_gray8(ctx, nullptr, (const float*)img.pixel(win.x1, win.y1), img.rowBytes, nc, d_gray, W, W, H));
         return;
     }
-    if (device_ptrs) throw StatusException{kOfxStatErrUnsupported};
-    check_cv(ofxcv_synchronize(ctx));  // the previous frame's upload out of `stage` must have left the pinned buffer
-    if (window_inside(win, img.bounds)) {  // the usual case: row copies by a few workers, overlapped with the H2D copies
-        upload_window(ctx, img, win, nc * 4, (char*)stage.p, d_float.p);
-        check_cv(ofxcv_rgba32f_to_srgb_gray8(ctx, nullptr, (const float*)d_float.p, (ptrdiff_t)W * nc * 4, nc, d_gray, W, W, H));
-        return;
-    }
-    float* s = (float*)stage.p;
-    const OfxRectI& b = img.bounds;
-    for (int y = win.y1; y < win.y2; y++) {
-        const int yy = y < b.y1 ? b.y1 : y >= b.y2 ? b.y2 - 1 : y;
-        float* out = s + (size_t)(y - win.y1) * W * nc;
-        const int xa = win.x1 > b.x1 ? win.x1 : b.x1, xb = win.x2 < b.x2 ? win.x2 : b.x2;  // overlap [xa, xb)
-        if (xb > xa) memcpy(out + (size_t)(xa - win.x1) * nc, img.pixel(xa, yy), (size_t)(xb - xa) * nc * 4);
-        for (int x = win.x1; x < win.x2; x++) {
-            if (x >= xa && x < xb) { x = xb - 1; continue; }
-            const int xx = x < b.x1 ? b.x1 : x >= b.x2 ? b.x2 - 1 : x;
-            memcpy(out + (size_t)(x - win.x1) * nc, img.pixel(xx, yy), (size_t)nc * 4);
+    if (window_inside(win, img.bounds)) {
+        upload_window(ctx, img, win, nc * 4, d_float.p);
+    } else {
+        PinBuf stage(ctx, 0, (size_t)W * H * nc * 4);
+        check_cv(ofxcv_synchronize(ctx));  // an earlier upload out of this pinned slot must have left it
+        float* s = (float*)stage.p;
+        const OfxRectI& b = img.bounds;
+        for (int y = win.y1; y < win.y2; y++) {
+            const int yy = y < b.y1 ? b.y1 : y >= b.y2 ? b.y2 - 1 : y;
+            float* out = s + (size_t)(y - win.y1) * W * nc;
+            const int xa = win.x1 > b.x1 ? win.x1 : b.x1, xb = win.x2 < b.x2 ? win.x2 : b.x2;  // overlap [xa, xb)
+            if (xb > xa) memcpy(out + (size_t)(xa - win.x1) * nc, img.pixel(xa, yy), (size_t)(xb - xa) * nc * 4);
+            for (int x = win.x1; x < win.x2; x++) {
+                if (x >= xa && x < xb) { x = xb - 1; continue; }
+                const int xx = x < b.x1 ? b.x1 : x >= b.x2 ? b.x2 - 1 : x;
+                memcpy(out + (size_t)(x - win.x1) * nc, img.pixel(xx, yy), (size_t)nc * 4);
+            }
         }
+        check_cv(ofxcv_upload(ctx, nullptr, d_float.p, s, (size_t)W * H * nc * 4));
     }
-    check_cv(ofxcv_upload(ctx, nullptr, d_float.p, s, (size_t)W * H * nc * 4));
     check_cv(ofxcv_rgba32f_to_srgb_gray8(ctx, nullptr, (const float*)d_float.p, (ptrdiff_t)W * nc * 4, nc, d_gray, W, W, H));
 }
+
+// the staged gray frame of an image + its content key: from the cache of staged frames when the host labels its images
+// (kOfxImagePropUniqueIdentifier), else staged into `own` (a scratch plane of the render)
+struct StagedFrame {
+    GrayCache::Entry* entry = nullptr;
+    const uint8_t* gray = nullptr;
+    uint64_t key = 0;
+    ~StagedFrame() { gGray.release(entry); }
+};
+void get_gray(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, bool dev, DevBuf& d_float, uint8_t* own, StagedFrame& out)
+{
+    const int W = win.x2 - win.x1, H = win.y2 - win.y1;
+    const int device = ofxcv_device(ctx);
+    if ((out.entry = gGray.find(img.uid, win, device))) {
+        out.gray = (const uint8_t*)out.entry->gray;
+        out.key = out.entry->key;
+        return;
+    }
+    out.entry = gGray.claim(ctx, img.uid, win, (size_t)W * H);
+    uint8_t* dstp = out.entry ? (uint8_t*)out.entry->gray : own;
+    stage_gray(ctx, img, win, dev, d_float, dstp);
+    check_cv(ofxcv_content_key_u8(ctx, nullptr, dstp, W, W, H, &out.key));  // synchronises: the plane is complete
+    if (out.entry) out.entry->key = out.key;
+    out.gray = dstp;
+}
+
+int abort_cb(void* effect) { return gHost.effect->abort((OfxImageEffectHandle)effect); }
 
 OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
 {
     Instance* d = instance_data(effect);
     RenderArgs a = render_args(gHost, inArgs);
     ImageGuard dst(gHost, d->dst, a.time);
+    // VectorGenerator.cpp:531-536: an output image whose scale or field is not the one being rendered fails the render
+    if (dst.img.scale.x != a.scale.x || dst.img.scale.y != a.scale.y || (!a.field.empty() && !dst.img.field.empty() && dst.img.field != a.field))
+        return kOfxStatFailed;
     if (dst.img.depth != kOfxBitDepthFloat || dst.img.components != kOfxImageComponentRGBA) return kOfxStatErrImageFormat;
     ImageGuard ref(gHost, d->src, a.time);  // missing image -> kOfxStatFailed (VectorGenerator.cpp:539-544)
     int ch[4];
@@ -216,49 +250,60 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
     const int W = win.x2 - win.x1, H = win.y2 - win.y1;
     const size_t n = (size_t)W * H;
     const bool dev = a.cudaEnabled != 0;
+    // CUDA render: the context of the GPU that owns the host's images (a host pointer here is a host bug -> unsupported)
+    int device = -1;
+    if (dev) {
+        device = ofxcv_pointer_device(dst.img.data);
+        if (device < 0) return kOfxStatErrUnsupported;
+    }
 
-    ContextLease lease(gPool);
+    ContextLease lease(gPool, device);
     ofxcv_ctx* ctx = lease.ctx;
-    PinBuf stage(ctx, 0, dev ? 16 : n * 16);
+    SyncOnExit sync(dev ? ctx : nullptr);  // nothing may still write into (or read from) the host's device images when we leave
+    ofxcv_set_abort_callback(ctx, abort_cb, effect);  // polled between pyramid scales inside the flow calls
     DevBuf d_float(ctx, 0, dev ? 16 : n * 16), d_gray0(ctx, 1, n), d_gray1(ctx, 2, n), d_flow(ctx, 3, n * 8), d_dst(ctx, 4, dev ? 16 : n * 16);
     float* out_dev = dev ? (float*)dst.img.pixel(win.x1, win.y1) : (float*)d_dst.p;
     const ptrdiff_t out_stride = dev ? dst.img.rowBytes : (ptrdiff_t)W * 16;
-    stage_gray(ctx, ref.img, win, dev, stage, d_float, (uint8_t*)d_gray0.p);
     // content keys: the pyramid of a gray frame is shared by the forward and the backward flow of this render and
     // by the neighbouring renders of the clip (frame t+1 here is frame t of the next render)
-    uint64_t key0 = 0;
-    check_cv(ofxcv_content_key_u8(ctx, nullptr, (const uint8_t*)d_gray0.p, W, W, H, &key0));
+    StagedFrame f0;
+    get_gray(ctx, ref.img, win, dev, d_float, (uint8_t*)d_gray0.p, f0);
     // channels set to "0" must read 0: scatter a zero flow into all four channels first
     check_cv(ofxcv_memset(ctx, nullptr, d_flow.p, 0, n * 8));
     {
         const int all[4] = {0, 0, 0, 0};
         check_cv(ofxcv_flow_to_rgba32f(ctx, nullptr, (const float*)d_flow.p, (ptrdiff_t)W * 8, out_dev, out_stride, W, H, all, 1.0, 1.0));
     }
-    for (int dir = 0; dir < 2; dir++) {
+    bool aborted = false;
+    for (int dir = 0; dir < 2 && !aborted; dir++) {
         if (!(dir == 0 ? fwd : bwd)) continue;
-        if (gHost.effect->abort(effect)) return kOfxStatOK;
+        if (gHost.effect->abort(effect)) break;
         ImageGuard other(gHost, d->src, dir == 0 ? a.time + 1 : a.time - 1);
-        stage_gray(ctx, other.img, win, dev, stage, d_float, (uint8_t*)d_gray1.p);
-        if (method == 1) {
-            check_cv(ofxcv_tvl1_u8(ctx, nullptr, (const uint8_t*)d_gray0.p, (const uint8_t*)d_gray1.p, W, W, H, (float*)d_flow.p,
-                                   (ptrdiff_t)W * 8, &tv));
-        } else {
-            uint64_t key1 = 0;
-            check_cv(ofxcv_content_key_u8(ctx, nullptr, (const uint8_t*)d_gray1.p, W, W, H, &key1));
-            check_cv(ofxcv_farneback_u8_keyed(ctx, nullptr, (const uint8_t*)d_gray0.p, (const uint8_t*)d_gray1.p, W, W, H,
-                                              (float*)d_flow.p, (ptrdiff_t)W * 8, &par, key0, key1));
+        SyncOnExit sync_other(dev ? ctx : nullptr);
+        StagedFrame f1;
+        get_gray(ctx, other.img, win, dev, d_float, (uint8_t*)d_gray1.p, f1);
+        int st;
+        if (method == 1)
+            st = ofxcv_tvl1_u8(ctx, nullptr, f0.gray, f1.gray, W, W, H, (float*)d_flow.p, (ptrdiff_t)W * 8, &tv);
+        else
+            st = ofxcv_farneback_u8_keyed(ctx, nullptr, f0.gray, f1.gray, W, W, H, (float*)d_flow.p, (ptrdiff_t)W * 8, &par, f0.key, f1.key);
+        if (st == OFXCV_ABORTED) {
+            aborted = true;
+            break;
         }
+        check_cv(st);
         int sel[4];
         const int u = dir == 0 ? 1 : 3, v = dir == 0 ? 2 : 4;
         for (int c = 0; c < 4; c++) sel[c] = ch[c] == u ? 0 : ch[c] == v ? 1 : -1;
         check_cv(ofxcv_flow_to_rgba32f(ctx, nullptr, (const float*)d_flow.p, (ptrdiff_t)W * 8, out_dev, out_stride, W, H, sel, a.scale.x,
                                        a.scale.y));
     }
-    if (!dev) {
-        download_window(ctx, dst.img, win, 16, (char*)stage.p, d_dst.p);
-    } else {
+    if (aborted || gHost.effect->abort(effect)) {  // like the reference's `if (abort()) return;` -- after the queue has drained
         check_cv(ofxcv_synchronize(ctx));
+        return kOfxStatOK;
     }
+    if (!dev) download_window(ctx, dst.img, win, 16, d_dst.p);
+    else check_cv(ofxcv_synchronize(ctx));
     return kOfxStatOK;
 }
 
@@ -300,6 +345,10 @@ OfxStatus plugin_main(const char* action, const void* handle, OfxPropertySetHand
         OfxImageEffectHandle effect = (OfxImageEffectHandle)handle;
         if (!strcmp(action, kOfxActionLoad)) return gHost.fetch();
         if (!strcmp(action, kOfxActionUnload)) {
+            if (ofxcv_device_count() > 0) {
+                ContextLease lease(gPool);
+                gGray.clear(lease.ctx);
+            }
             gPool.clear();
             return kOfxStatOK;
         }

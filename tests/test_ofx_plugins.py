@@ -341,3 +341,85 @@ def test_inpaint_plugin_large_host_images(mh, pkg, ctx, synth, flip):
     got = dst if not flip else dst[::-1]
     assert np.array_equal(got[..., :3], ref) and (got[..., 3] == 255).all()
     p.close()
+
+
+def _bundle_lib(mh, name):
+    """The private libofxcv_b200.so of a bundle (already loaded by the plugin; CDLL of the same path is the same instance)."""
+    import ctypes as C
+    import os
+    L = C.CDLL(os.path.join(os.path.dirname(mh.bundle_path(name)), "libofxcv_b200.so"))
+    L.ofxcv_transfer_stats.restype = None
+    L.ofxcv_transfer_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    return L
+
+
+@pytest.mark.gpu
+def test_vectorgenerator_render_argument_checks(mh, oracle, synth):
+    """VectorGenerator.cpp:531-536: an output image whose render scale or field differs from the render arguments fails the
+    render; a CUDA-enabled render handed host pointers is refused; abort leaves with kOfxStatOK and no image outstanding."""
+    h, w = 64, 80
+    base = synth.gray(synth.texture(h, w, 5))
+    frames = {t: _float_rgba(synth, oracle, synth.shift_bilinear(base, 1.0 * t, 0.5 * t)) for t in (1, 2, 3)}
+    p = mh.Plugin("VectorGenerator")
+    assert p.create_instance() == 0
+    for t, f in frames.items():
+        p.set_image("Source", t, f)
+    dst = np.zeros((h, w, 4), np.float32)
+    p.set_image("Output", 2, dst)
+    assert p.render(2, (0, 0, w, h)) == 0
+    p.set_image_props("Output", 2, scale=(0.5, 0.5))
+    assert p.render(2, (0, 0, w, h)) == mh.STAT_FAILED and p.images_outstanding() == 0      # scale (1,1) rendered into a half-scale image
+    assert p.render(2, (0, 0, w, h), scale=(0.5, 0.5)) == 0
+    p.set_image_props("Output", 2, scale=(1.0, 1.0), field="OfxFieldLower")
+    assert p.render(2, (0, 0, w, h)) == mh.STAT_FAILED and p.images_outstanding() == 0      # field None rendered into a lower-field image
+    p.set_image_props("Output", 2)
+    assert p.render(2, (0, 0, w, h), cuda_enabled=1) == mh.STAT_ERR_UNSUPPORTED and p.images_outstanding() == 0   # host pointers are not device images
+    good = dst.copy()
+    p.set_abort(1)
+    dst[...] = -5.0
+    assert p.render(2, (0, 0, w, h)) == 0 and p.images_outstanding() == 0
+    p.set_abort(0)
+    assert p.render(2, (0, 0, w, h)) == 0 and np.array_equal(dst, good)
+    p.close()
+
+
+@pytest.mark.gpu
+def test_vectorgenerator_keeps_staged_frames_between_renders(mh, oracle, synth):
+    """getFramesNeeded (VectorGenerator.cpp:675-695) makes render t+1 refetch two of render t's three frames: with images
+    labelled by the host (kOfxImagePropUniqueIdentifier) the second render uploads ONE new frame, not three, and gives the
+    same pixels as a host that does not label its images."""
+    h, w = 90, 120
+    base = synth.gray(synth.texture(h, w, 9))
+    frames = {t: _float_rgba(synth, oracle, synth.shift_bilinear(base, 1.25 * t, -0.5 * t)) for t in range(1, 6)}
+    L = _bundle_lib(mh, "VectorGenerator")
+    frame_bytes = w * h * 16
+
+    def h2d():
+        import ctypes as C
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        L.ofxcv_transfer_stats(C.byref(a), C.byref(b))
+        return int(a.value)
+
+    outs = {}
+    for labelled in (True, False):
+        mh.Plugin.provide_unique_identifiers(labelled)
+        p = mh.Plugin("VectorGenerator")
+        assert p.create_instance() == 0
+        for t, f in frames.items():
+            p.set_image("Source", t, f)
+        per_render = []
+        for t in (2, 3, 4):
+            dst = np.zeros((h, w, 4), np.float32)
+            p.clear_images("Output"); p.set_image("Output", t, dst)
+            before = h2d()
+            assert p.render(t, (0, 0, w, h)) == 0 and p.images_outstanding() == 0
+            per_render.append(h2d() - before)
+            outs[(labelled, t)] = dst
+        p.close()
+        if labelled:
+            assert per_render == [3 * frame_bytes, frame_bytes, frame_bytes], per_render
+        else:
+            assert per_render == [3 * frame_bytes] * 3, per_render
+    mh.Plugin.provide_unique_identifiers(True)
+    for t in (2, 3, 4):
+        assert np.array_equal(outs[(True, t)], outs[(False, t)])
