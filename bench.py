@@ -446,8 +446,9 @@ def run_flow(args, wl):
         if world == 1 and not args.no_cpu:
             cpu_baseline_leg(args, line)
         if world == 1 and args.workload == "farneback_4k" and not args.no_plugins:
-            try:
-                line["e2e_plugin"] = bench_plugin_boundary(pkg, synth, ctx, W, H)
+            try:   # in a process of its own: the host-side row copies of the glue must not share cores with this process's thread pools
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--plugin-leg"], capture_output=True, text=True, timeout=900)
+                line["e2e_plugin"] = json.loads(out.stdout.strip().splitlines()[-1])
             except Exception as e:
                 line["e2e_plugin"] = {"error": repr(e)}
             try:
@@ -879,8 +880,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-plugins", action="store_true", help="skip the plugin-boundary and other-plugin entries")
     ap.add_argument("--no-parity", action="store_true", help="skip the comparison of output 0 with the reference's OpenCV call")
+    ap.add_argument("--plugin-leg", action="store_true", help=argparse.SUPPRESS)   # internal: the e2e_plugin entry, run as a subprocess
     args = ap.parse_args()
     args.out = OneLineStdout()
+    if args.plugin_leg:
+        pkg = importlib.import_module("openfx-opencv_b200")
+        synth = importlib.import_module("openfx-opencv_b200.synth")
+        ctx = pkg.Context(int(os.environ.get("LOCAL_RANK", "0")))
+        args.out.emit(json.dumps(bench_plugin_boundary(pkg, synth, ctx, 3840, 2160)))
+        return 0
     if args.impl == "reference":
         return run_reference(args)
     wl = WORKLOADS[args.workload]

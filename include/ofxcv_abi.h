@@ -98,6 +98,12 @@ OFXCV_API int ofxcv_upload_rows(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, c
                                 size_t row_bytes, int rows);
 OFXCV_API int ofxcv_download_rows(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_host, ptrdiff_t dst_stride, const void* src_dev,
                                   size_t row_bytes, int rows);
+/* A second stream of the context for staging work that should overlap the compute on the main stream (the OFX glue uploads
+ * and converts frame t+1 on it while the backward flow of frames t, t-1 runs), and the two ordering primitives that
+ * go with it: `waiter` waits for everything enqueued on `signaller` so far; synchronise one stream.  NULL = main stream. */
+OFXCV_API ofxcv_stream ofxcv_aux_stream(ofxcv_ctx* ctx);
+OFXCV_API int ofxcv_stream_wait(ofxcv_ctx* ctx, ofxcv_stream waiter, ofxcv_stream signaller);
+OFXCV_API int ofxcv_stream_synchronize(ofxcv_ctx* ctx, ofxcv_stream s);
 /* bytes moved host->device / device->host by the staging helpers of this library since it was loaded (all contexts) */
 OFXCV_API void ofxcv_transfer_stats(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 /* abort polling (the host's OfxImageEffectSuiteV1::abort, /root/reference/openfx/include/ofxImageEffect.h): when set, the

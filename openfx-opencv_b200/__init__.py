@@ -101,6 +101,9 @@ def lib():
         "ofxcv_download": (i, [vp, vp, vp, vp, sz]),
         "ofxcv_device_copy": (i, [vp, vp, vp, vp, sz]),
         "ofxcv_memset": (i, [vp, vp, vp, i, sz]),
+        "ofxcv_aux_stream": (vp, [vp]),
+        "ofxcv_stream_wait": (i, [vp, vp, vp]),
+        "ofxcv_stream_synchronize": (i, [vp, vp]),
         "ofxcv_current_device": (i, []),
         "ofxcv_pointer_device": (i, [vp]),
         "ofxcv_upload_rows": (i, [vp, vp, vp, vp, pd, sz, i]),

@@ -43,7 +43,7 @@ struct ofxcv_ctx {
     // named device workspaces, grown on demand, reused between calls
     ofxcv_buf ws[72];
     // pinned host staging for the *_host entry points
-    ofxcv_buf pin[14];  // 0-3 internal staging, 4-11 ofxcv_scratch_pinned, 12 Dual TV-L1 stop flags, 13 watershed round counters
+    ofxcv_buf pin[15];  // 0-3 internal staging, 4-11 ofxcv_scratch_pinned, 12 Dual TV-L1 stop flags, 13 watershed round counters, 14 content keys
     // per-family kernel timing (bench.py roofline numerator): events recorded on the launching stream
     bool timing = false;
     std::vector<ofxcv_timed_launch> timed[3];
@@ -72,6 +72,7 @@ struct ofxcv_ctx {
     size_t tv_ctrl_off = 0;  // where the last ofxcv_tvl1_u8 put its control block inside WS_TV_ARENA
     std::vector<cudaEvent_t> xfer_ev;     // chunk events of ofxcv_download_rows
     cudaEvent_t xfer_up_done = nullptr;   // the last DMA out of the upload staging buffer
+    cudaEvent_t order_ev = nullptr;       // ofxcv_stream_wait
     int (*abort_cb)(void*) = nullptr;     // polled between pyramid scales / pairs / frames (ofxcv_set_abort_callback)
     void* abort_user = nullptr;
     int64_t inpaint_stats[4] = {0, 0, 0, 0};
@@ -216,6 +217,7 @@ enum {
     WS_FB3_TOT,
     WS_TV_ARENA,  // Dual TV-L1: pyramids + J/A/P/U planes + control block, one allocation
     WS_WSP_ARENA, // parallel watershed: claims, records, level queues, sort buffers, one allocation
+    WS_KEY,       // content-key accumulators
     WS_COUNT
 };
 static_assert(WS_COUNT + 8 <= 72, "workspace slots (the last 8 are ofxcv_scratch_device)");

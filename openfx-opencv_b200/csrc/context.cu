@@ -1,4 +1,6 @@
 // Context, memory and timing plumbing of the C ABI (include/ofxcv_abi.h).  No image arithmetic here.
+#include <stdlib.h>
+
 #include <atomic>
 #include <thread>
 
@@ -9,8 +11,10 @@ static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
 namespace {
 int xfer_workers()
 {
+    static const int forced = getenv("OFXCV_XFER_THREADS") ? atoi(getenv("OFXCV_XFER_THREADS")) : 0;
+    if (forced > 0) return forced;
     const unsigned hc = std::thread::hardware_concurrency();
-    return hc >= 8 ? 4 : hc >= 4 ? 2 : 1;
+    return hc >= 32 ? 8 : hc >= 8 ? 4 : hc >= 4 ? 2 : 1;
 }
 // runs work() on up to n threads; a thread that cannot be created is replaced by the calling thread doing the work
 template <class F>
@@ -179,6 +183,7 @@ void ofxcv_destroy(ofxcv_ctx* ctx)
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->xfer_ev) cudaEventDestroy(e);
     if (ctx->xfer_up_done) cudaEventDestroy(ctx->xfer_up_done);
+    if (ctx->order_ev) cudaEventDestroy(ctx->order_ev);
     for (int f = 0; f < 3; f++)
         for (auto& t : ctx->timed[f]) {
             cudaEventDestroy(t.a);
@@ -378,6 +383,35 @@ int ofxcv_memset(ofxcv_ctx* ctx, ofxcv_stream s, void* dst_dev, int value, size_
     if (!dst_dev) return OFXCV_ERR_BAD_ARG;
     ofxcv_device_guard g(ctx->device);
     OFXCV_CUDA(ctx, cudaMemsetAsync(dst_dev, value, bytes, pick(ctx, s)));
+    return OFXCV_OK;
+}
+
+ofxcv_stream ofxcv_aux_stream(ofxcv_ctx* ctx)
+{
+    if (!ctx) return nullptr;
+    ofxcv_device_guard g(ctx->device);
+    if (!ctx->stream_up && cudaStreamCreateWithFlags(&ctx->stream_up, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return (ofxcv_stream)ctx->stream_up;
+}
+
+int ofxcv_stream_wait(ofxcv_ctx* ctx, ofxcv_stream waiter, ofxcv_stream signaller)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    ofxcv_device_guard g(ctx->device);
+    if (!ctx->order_ev) OFXCV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming));
+    OFXCV_CUDA(ctx, cudaEventRecord(ctx->order_ev, pick(ctx, signaller)));
+    OFXCV_CUDA(ctx, cudaStreamWaitEvent(pick(ctx, waiter), ctx->order_ev, 0));
+    return OFXCV_OK;
+}
+
+int ofxcv_stream_synchronize(ofxcv_ctx* ctx, ofxcv_stream s)
+{
+    if (!ctx) return OFXCV_ERR_NO_DEVICE;
+    ofxcv_device_guard g(ctx->device);
+    OFXCV_CUDA(ctx, cudaStreamSynchronize(pick(ctx, s)));
     return OFXCV_OK;
 }
 

@@ -361,20 +361,33 @@ __global__ void __launch_bounds__(256) cv_rgb_to_rgba_noise(const uint8_t* __res
     q[3] = 255;
 }
 
-// position-sensitive 64-bit content hash of a u8 plane: sum over pixels of splitmix64(value + golden * (index+1))
+// position-sensitive content hash of a u8 plane, two independent 64-bit lanes: lane k = sum over pixels of
+// mix_k(value + golden * (index+1)) (splitmix64 / murmur3 finalisers with different constants)
 __global__ void __launch_bounds__(256) cv_content_key(const uint8_t* __restrict__ img, ptrdiff_t stride, int W, int H,
                                                       unsigned long long* __restrict__ acc)
 {
-    unsigned long long sum = 0;
+    unsigned long long sum = 0, sum2 = 0;
     const int y = blockIdx.y;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
-        unsigned long long z = (unsigned long long)img[(size_t)y * stride + x] + 0x9E3779B97F4A7C15ull * ((unsigned long long)y * W + x + 1);
+        const unsigned long long v = (unsigned long long)img[(size_t)y * stride + x];
+        const unsigned long long idx = (unsigned long long)y * W + x + 1;
+        unsigned long long z = v + 0x9E3779B97F4A7C15ull * idx;
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         sum += z ^ (z >> 31);
+        unsigned long long u = (v << 56) ^ (0xD6E8FEB86659FD93ull * idx);
+        u = (u ^ (u >> 33)) * 0xFF51AFD7ED558CCDull;
+        u = (u ^ (u >> 33)) * 0xC4CEB9FE1A85EC53ull;
+        sum2 += u ^ (u >> 33);
     }
-    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
-    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(acc, sum);
+    for (int d = 16; d > 0; d >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, d);
+        sum2 += __shfl_down_sync(0xffffffffu, sum2, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (sum) atomicAdd(acc, sum);
+        if (sum2) atomicAdd(acc + 1, sum2);
+    }
 }
 
 __global__ void __launch_bounds__(256) cv_seed_grid(int32_t* __restrict__ m, ptrdiff_t ms, int W, int H, int gx, int gy, int half)
@@ -596,15 +609,18 @@ int ofxcv_content_key_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* img
     if (!img || !key || W <= 0 || H <= 0 || stride < W) return OFXCV_ERR_BAD_ARG;
     ofxcv_device_guard guard(ctx->device);
     cudaStream_t s = pick(ctx, stream);
-    unsigned long long* acc = (unsigned long long*)ofxcv_ws(ctx, WS_MISC2, 8);
-    unsigned long long* host = (unsigned long long*)ofxcv_pin(ctx, 3, 8);
+    unsigned long long* acc = (unsigned long long*)ofxcv_ws(ctx, WS_KEY, 16);   // own slots: keys are taken on the staging stream too
+    unsigned long long* host = (unsigned long long*)ofxcv_pin(ctx, 14, 16);
     if (!acc || !host) return OFXCV_ERR_MEMORY;
-    OFXCV_CUDA(ctx, cudaMemsetAsync(acc, 0, 8, s));
+    OFXCV_CUDA(ctx, cudaMemsetAsync(acc, 0, 16, s));
     cv_content_key<<<dim3(ofxcv_div_up(W, 1024) > 0 ? ofxcv_div_up(W, 1024) : 1, H), 256, 0, s>>>(img, stride, W, H, acc);
     OFXCV_LAUNCH_CHECK(ctx);
-    OFXCV_CUDA(ctx, cudaMemcpyAsync(host, acc, 8, cudaMemcpyDeviceToHost, s));
+    OFXCV_CUDA(ctx, cudaMemcpyAsync(host, acc, 16, cudaMemcpyDeviceToHost, s));
     OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
-    uint64_t k = (uint64_t)*host ^ ((uint64_t)W << 40) ^ ((uint64_t)H << 20);
+    // fold the two lanes and the geometry; a collision needs both independent 64-bit sums to agree
+    uint64_t a = (uint64_t)host[0], b = (uint64_t)host[1] + 0x9E3779B97F4A7C15ull * (((uint64_t)W << 32) | (uint64_t)H);
+    b = (b ^ (b >> 29)) * 0xBF58476D1CE4E5B9ull;
+    uint64_t k = a ^ (b ^ (b >> 32));
     *key = k ? k : 1;
     return OFXCV_OK;
 }

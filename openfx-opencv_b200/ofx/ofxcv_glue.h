@@ -142,7 +142,9 @@ struct SyncOnExit {
     explicit SyncOnExit(ofxcv_ctx* c) : ctx(c) {}
     ~SyncOnExit()
     {
-        if (ctx) ofxcv_synchronize(ctx);
+        if (!ctx) return;
+        ofxcv_stream_synchronize(ctx, ofxcv_aux_stream(ctx));  // staging stream (conversions read the host's device images)
+        ofxcv_synchronize(ctx);
     }
     SyncOnExit(const SyncOnExit&) = delete;
 };

@@ -12,7 +12,10 @@
 // Deliberate differences, all documented in DESIGN.md: channels set to "0" are written as 0.0 (the reference leaves
 // them uninitialised); the whole row is converted (the pinned reference converts a quarter: SURVEY.md B1).
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <chrono>
 
 #include "ofxcv_glue.h"
 
@@ -151,7 +154,7 @@ void read_channels(Instance* d, OfxTime t, int ch[4], bool& fwd, bool& bwd)
 // one frame -> 8-bit sRGB gray on the device.  Host images: the render window goes to the device through the row
 // pipeline of the C ABI (or, when it sticks out of the image bounds, is gathered replicate-clamped first =
 // copyMakeBorder(BORDER_REPLICATE) to the union bounds, VectorGenerator.cpp:387-388), then one conversion kernel.
-void stage_gray(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, bool device_ptrs, DevBuf& d_float, uint8_t* d_gray)
+void stage_gray(ofxcv_ctx* ctx, ofxcv_stream s, const Image& img, const OfxRectI& win, bool device_ptrs, DevBuf& d_float, uint8_t* d_gray)
 {
     const int W = win.x2 - win.x1, H = win.y2 - win.y1, nc = img.ncomp();
     if (img.depth != kOfxBitDepthFloat) throw StatusException{kOfxStatErrImageFormat};
@@ -159,19 +162,19 @@ void stage_gray(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, bool devi
         if (!window_inside(win, img.bounds)) throw StatusException{kOfxStatErrUnsupported};
         // the host's device image must live on the GPU this context runs on (multi-GPU hosts render on several)
         if (ofxcv_pointer_device(img.data) != ofxcv_device(ctx)) throw StatusException{kOfxStatErrUnsupported};
-        check_cv(ofxcv_rgba32f_to_srgb_gray8(ctx, nullptr, (const float*)img.pixel(win.x1, win.y1), img.rowBytes, nc, d_gray, W, W, H));
+        check_cv(ofxcv_rgba32f_to_srgb_gray8(ctx, s, (const float*)img.pixel(win.x1, win.y1), img.rowBytes, nc, d_gray, W, W, H));
         return;
     }
     if (window_inside(win, img.bounds)) {
-        upload_window(ctx, img, win, nc * 4, d_float.p);
+        check_cv(ofxcv_upload_rows(ctx, s, d_float.p, img.pixel(win.x1, win.y1), img.rowBytes, (size_t)W * nc * 4, H));
     } else {
         PinBuf stage(ctx, 0, (size_t)W * H * nc * 4);
-        check_cv(ofxcv_synchronize(ctx));  // an earlier upload out of this pinned slot must have left it
-        float* s = (float*)stage.p;
+        check_cv(ofxcv_stream_synchronize(ctx, s));  // an earlier upload out of this pinned slot must have left it
+        float* sp = (float*)stage.p;
         const OfxRectI& b = img.bounds;
         for (int y = win.y1; y < win.y2; y++) {
             const int yy = y < b.y1 ? b.y1 : y >= b.y2 ? b.y2 - 1 : y;
-            float* out = s + (size_t)(y - win.y1) * W * nc;
+            float* out = sp + (size_t)(y - win.y1) * W * nc;
             const int xa = win.x1 > b.x1 ? win.x1 : b.x1, xb = win.x2 < b.x2 ? win.x2 : b.x2;  // overlap [xa, xb)
             if (xb > xa) memcpy(out + (size_t)(xa - win.x1) * nc, img.pixel(xa, yy), (size_t)(xb - xa) * nc * 4);
             for (int x = win.x1; x < win.x2; x++) {
@@ -180,9 +183,9 @@ void stage_gray(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, bool devi
                 memcpy(out + (size_t)(x - win.x1) * nc, img.pixel(xx, yy), (size_t)nc * 4);
             }
         }
-        check_cv(ofxcv_upload(ctx, nullptr, d_float.p, s, (size_t)W * H * nc * 4));
+        check_cv(ofxcv_upload(ctx, s, d_float.p, stage.p, (size_t)W * H * nc * 4));
     }
-    check_cv(ofxcv_rgba32f_to_srgb_gray8(ctx, nullptr, (const float*)d_float.p, (ptrdiff_t)W * nc * 4, nc, d_gray, W, W, H));
+    check_cv(ofxcv_rgba32f_to_srgb_gray8(ctx, s, (const float*)d_float.p, (ptrdiff_t)W * nc * 4, nc, d_gray, W, W, H));
 }
 
 // the staged gray frame of an image + its content key: from the cache of staged frames when the host labels its images
@@ -193,8 +196,11 @@ struct StagedFrame {
     uint64_t key = 0;
     ~StagedFrame() { gGray.release(entry); }
 };
+// staging (upload, conversion, key) runs on the context's staging stream, so that it overlaps whatever flow is already
+// queued on the main stream; the main stream is made to wait for it before the caller enqueues anything that reads the plane
 void get_gray(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, bool dev, DevBuf& d_float, uint8_t* own, StagedFrame& out)
 {
+    ofxcv_stream aux = ofxcv_aux_stream(ctx);
     const int W = win.x2 - win.x1, H = win.y2 - win.y1;
     const int device = ofxcv_device(ctx);
     if ((out.entry = gGray.find(img.uid, win, device))) {
@@ -204,11 +210,25 @@ void get_gray(ofxcv_ctx* ctx, const Image& img, const OfxRectI& win, bool dev, D
     }
     out.entry = gGray.claim(ctx, img.uid, win, (size_t)W * H);
     uint8_t* dstp = out.entry ? (uint8_t*)out.entry->gray : own;
-    stage_gray(ctx, img, win, dev, d_float, dstp);
-    check_cv(ofxcv_content_key_u8(ctx, nullptr, dstp, W, W, H, &out.key));  // synchronises: the plane is complete
+    stage_gray(ctx, aux, img, win, dev, d_float, dstp);
+    check_cv(ofxcv_content_key_u8(ctx, aux, dstp, W, W, H, &out.key));  // synchronises the staging stream: the plane is complete
     if (out.entry) out.entry->key = out.key;
     out.gray = dstp;
 }
+
+// OFXCV_TRACE=1: wall-clock of the phases of a render on stderr (what tools/plugin_render_time.py reads)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("OFXCV_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what)
+    {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[vg] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t0).count());
+        t0 = t;
+    }
+};
 
 int abort_cb(void* effect) { return gHost.effect->abort((OfxImageEffectHandle)effect); }
 
@@ -262,12 +282,15 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
     SyncOnExit sync(dev ? ctx : nullptr);  // nothing may still write into (or read from) the host's device images when we leave
     ofxcv_set_abort_callback(ctx, abort_cb, effect);  // polled between pyramid scales inside the flow calls
     DevBuf d_float(ctx, 0, dev ? 16 : n * 16), d_gray0(ctx, 1, n), d_gray1(ctx, 2, n), d_flow(ctx, 3, n * 8), d_dst(ctx, 4, dev ? 16 : n * 16);
+    DevBuf d_gray2(ctx, 5, n);  // one plane per neighbour frame: t-1 may still be read by the backward flow while t+1 is staged
     float* out_dev = dev ? (float*)dst.img.pixel(win.x1, win.y1) : (float*)d_dst.p;
     const ptrdiff_t out_stride = dev ? dst.img.rowBytes : (ptrdiff_t)W * 16;
     // content keys: the pyramid of a gray frame is shared by the forward and the backward flow of this render and
     // by the neighbouring renders of the clip (frame t+1 here is frame t of the next render)
+    Trace tr;
     StagedFrame f0;
     get_gray(ctx, ref.img, win, dev, d_float, (uint8_t*)d_gray0.p, f0);
+    tr.mark("frame t staged");
     // channels set to "0" must read 0: scatter a zero flow into all four channels first
     check_cv(ofxcv_memset(ctx, nullptr, d_flow.p, 0, n * 8));
     {
@@ -275,13 +298,17 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
         check_cv(ofxcv_flow_to_rgba32f(ctx, nullptr, (const float*)d_flow.p, (ptrdiff_t)W * 8, out_dev, out_stride, W, H, all, 1.0, 1.0));
     }
     bool aborted = false;
-    for (int dir = 0; dir < 2 && !aborted; dir++) {
+    // backward first: frames t and t-1 are usually staged already (render t-1 needed them), so its solve is queued at once
+    // and runs while frame t+1 is uploaded and converted on the staging stream
+    for (int pass = 0; pass < 2 && !aborted; pass++) {
+        const int dir = 1 - pass;
         if (!(dir == 0 ? fwd : bwd)) continue;
         if (gHost.effect->abort(effect)) break;
         ImageGuard other(gHost, d->src, dir == 0 ? a.time + 1 : a.time - 1);
         SyncOnExit sync_other(dev ? ctx : nullptr);
         StagedFrame f1;
-        get_gray(ctx, other.img, win, dev, d_float, (uint8_t*)d_gray1.p, f1);
+        get_gray(ctx, other.img, win, dev, d_float, (uint8_t*)(dir == 0 ? d_gray1.p : d_gray2.p), f1);
+        tr.mark(dir == 0 ? "frame t+1 staged" : "frame t-1 staged");
         int st;
         if (method == 1)
             st = ofxcv_tvl1_u8(ctx, nullptr, f0.gray, f1.gray, W, W, H, (float*)d_flow.p, (ptrdiff_t)W * 8, &tv);
@@ -297,6 +324,7 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
         for (int c = 0; c < 4; c++) sel[c] = ch[c] == u ? 0 : ch[c] == v ? 1 : -1;
         check_cv(ofxcv_flow_to_rgba32f(ctx, nullptr, (const float*)d_flow.p, (ptrdiff_t)W * 8, out_dev, out_stride, W, H, sel, a.scale.x,
                                        a.scale.y));
+        tr.mark("flow enqueued");
     }
     if (aborted || gHost.effect->abort(effect)) {  // like the reference's `if (abort()) return;` -- after the queue has drained
         check_cv(ofxcv_synchronize(ctx));
@@ -304,6 +332,7 @@ OfxStatus render(OfxImageEffectHandle effect, OfxPropertySetHandle inArgs)
     }
     if (!dev) download_window(ctx, dst.img, win, 16, d_dst.p);
     else check_cv(ofxcv_synchronize(ctx));
+    tr.mark(dev ? "synchronised" : "result downloaded");
     return kOfxStatOK;
 }
 

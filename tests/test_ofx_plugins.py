@@ -236,6 +236,7 @@ def test_vectorgenerator_plugin_render(mh, oracle, synth):
         p.set_image("Source", t, f)
     dst = np.full((h, w, 4), 7.0, np.float32)
     p.set_image("Output", 5, dst)
+    p.set_image_props("Output", 5, scale=(0.5, 0.25))     # the host renders at this scale: the output image carries it
     assert p.render(5, (0, 0, w, h), scale=(0.5, 0.25)) == 0 and p.images_outstanding() == 0
     fwd = oracle.farneback(g[5], g[6])
     bwd = oracle.farneback(g[5], g[4])
