@@ -368,6 +368,7 @@ def test_vectorgenerator_render_argument_checks(mh, oracle, synth):
     dst = np.zeros((h, w, 4), np.float32)
     p.set_image("Output", 2, dst)
     assert p.render(2, (0, 0, w, h)) == 0
+    good = dst.copy()
     p.set_image_props("Output", 2, scale=(0.5, 0.5))
     assert p.render(2, (0, 0, w, h)) == mh.STAT_FAILED and p.images_outstanding() == 0      # scale (1,1) rendered into a half-scale image
     assert p.render(2, (0, 0, w, h), scale=(0.5, 0.5)) == 0
@@ -375,7 +376,6 @@ def test_vectorgenerator_render_argument_checks(mh, oracle, synth):
     assert p.render(2, (0, 0, w, h)) == mh.STAT_FAILED and p.images_outstanding() == 0      # field None rendered into a lower-field image
     p.set_image_props("Output", 2)
     assert p.render(2, (0, 0, w, h), cuda_enabled=1) == mh.STAT_ERR_UNSUPPORTED and p.images_outstanding() == 0   # host pointers are not device images
-    good = dst.copy()
     p.set_abort(1)
     dst[...] = -5.0
     assert p.render(2, (0, 0, w, h)) == 0 and p.images_outstanding() == 0
