@@ -15,7 +15,16 @@ img = s.texture(60, 80, 1)
 for m in (p.INPAINT_NS, p.INPAINT_TELEA):
     ctx.inpaint(img, s.iid_mask(60, 80, 2, 0.1), 3, m)
     ctx.inpaint(img, s.blob_mask(60, 80, 3), 5, m)
-ctx.watershed(img, s.seed_markers(60, 80, 5, 5))
+ctx.watershed(img, s.seed_markers(60, 80, 5, 5))                       # one frame: the round-synchronous parallel flood
+noise = np.random.default_rng(9).integers(0, 256, (70, 90, 3), dtype=np.uint8)
+ctx.watershed(noise, s.seed_markers(70, 90, 6, 3))                    # levels above 32: the 256-level instantiation
+os.environ["OFXCV_WS_MODE"] = "seq"
+ctx.watershed(img, s.seed_markers(60, 80, 5, 5))                       # the one-thread flood (long clips)
+del os.environ["OFXCV_WS_MODE"]
+big = np.random.default_rng(3).random((300, 260, 4), dtype=np.float32)   # row-transfer pipeline (chunked) through the C ABI
+d_big = ctx.alloc(big.nbytes); back = np.zeros_like(big)
+ctx.upload_rows(d_big.ptr, big.ctypes.data, 260 * 16, 300, 260 * 16); ctx.download_rows(back.ctypes.data, 260 * 16, d_big.ptr, 260 * 16, 300)
+assert (big == back).all()
 rgba = np.random.default_rng(0).random((33, 47, 4), dtype=np.float32)
 ctx.rgba32f_to_srgb_gray8(rgba); ctx.rgba32f_to_srgb8_packed(rgba, 4); ctx.srgb8_packed_to_rgba32f((rgba * 255).astype(np.uint8))
 for (h, w) in ((20, 18), (61, 97), (130, 300)):
