@@ -259,7 +259,9 @@ class Rig:
         torch.cuda.set_device(self.local)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            import datetime
+            # a collective that does not complete within minutes is a bug of this script: fail fast instead of hanging the box
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local), timeout=datetime.timedelta(seconds=300))
         self.pkg = importlib.import_module("openfx-opencv_b200")
         self.synth = importlib.import_module("openfx-opencv_b200.synth")
         self.seq = importlib.import_module("openfx-opencv_b200.sequence")
@@ -392,8 +394,12 @@ def run_flow(args, wl):
     for _ in range(2):
         step_e2e()
     ms_e2e = rig.timed(step_e2e, args.steps)
-    pairs_all = rig.total(count) * args.steps
+    # every collective happens here, on every rank; below this point only rank 0 works
+    count_all = int(rig.total(count))
+    pairs_all = count_all * args.steps
     launches_all = rig.total(launches)
+    h2d_all = int(rig.total(sum(W * H * (n + 1) for n in calls)))
+    d2h_all = int(rig.total(sum(8 * W * H * n for n in calls)))
     sums = checksum_report(rig, keys)
     if rank == 0:
         value = pairs_all / (ms * 1e-3)
@@ -413,7 +419,7 @@ def run_flow(args, wl):
             "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic: Texture(seed 2000) translated by t*(2.5,-1.5) px; every rank's block holds frames t = 0..%d (periodic sequence)" % chunk,
-            "config": dict(workload_config(args.workload, wl, int(rig.total(count))), **{
+            "config": dict(workload_config(args.workload, wl, count_all), **{
                 "sharding": "contiguous frame blocks, one per GPU, 1-frame halo" + (" (clip of %d frames split over the ranks)" % args.clip_frames if strong else ""),
                 "call": "ofxcv_farneback_sequence_u8, %s pair(s) + 1 frames per call, %d call(s) per step and GPU; each frame's pyramid built once per call" % (
                     "/".join(str(n) for n in sorted(set(calls), reverse=True)), len(calls)),
@@ -433,8 +439,7 @@ def run_flow(args, wl):
                          "whole_pair_frac": step_bytes * args.steps / (ms * 1e-3) / 1e9 / peak,
                          "whole_pair_model": "per GPU: sum over calls of (n+1) frame pyramids x %.3f GB + n solves x %.3f GB (a stand-alone pair = %.3f GB)" % (
                              frame_bytes / 1e9, solve_bytes / 1e9, pair_model / 1e9)},
-            "e2e": {"value": pairs_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(rig.total(sum(W * H * (n + 1) for n in calls))),
-                    "d2h_bytes_per_step": int(rig.total(sum(8 * W * H * n for n in calls))),
+            "e2e": {"value": pairs_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                     "api": "ofxcv_farneback_sequence_u8_host, page-locked host frames, upload/compute/download on three streams"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
@@ -530,7 +535,8 @@ def run_inpaint(args, wl):
     n_fill, fill_ms = ctx.kernel_time_ms(1)
     step_e2e()
     ms_e2e = rig.timed(step_e2e, args.steps, blocking=True)
-    frames_all = rig.total(count) * args.steps
+    count_all = int(rig.total(count))   # every collective on every rank; below only rank 0 works
+    frames_all = count_all * args.steps
     launches_all = rig.total(launches)
     sums = checksum_report(rig, keys)
     if rank == 0:
@@ -542,7 +548,7 @@ def run_inpaint(args, wl):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "u8",
             "data": "synthetic: Texture(seed 4) RGB8, iid masks (seeds 1000+t), every rank's block holds the same %d distinct frames" % nd,
-            "config": dict(workload_config(args.workload, wl, int(rig.total(count))), **{
+            "config": dict(workload_config(args.workload, wl, count_all), **{
                 "sharding": "contiguous frame blocks, one per GPU, no halo" + (" (clip of %d frames split over the ranks)" % args.clip_frames if strong else ""),
                 "call": "ofxcv_inpaint_sequence_u8, %d frames per call, %d in flight" % (count, K),
                 "l2": "a 4K frame's working set (T map, flags, colours: ~100 MB per frame in flight) exceeds the 126 MB L2 with 8 frames in flight" if W * H > 4e6
@@ -553,8 +559,8 @@ def run_inpaint(args, wl):
                          "note": "the fill is bound by the dependency chain of the fast-marching order (thousands of steps deep), not by HBM: "
                                  "the fraction is reported because the contract asks for it, it is not a target"},
             "single_frame": {"ms": single_ms, "frames_per_s": 1e3 / single_ms, "call": "ofxcv_inpaint_u8 (what one render of the plugin runs)"},
-            "e2e": {"value": frames_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(rig.total(count * W * H * 4)),
-                    "d2h_bytes_per_step": int(rig.total(count * W * H * 3)),
+            "e2e": {"value": frames_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": count_all * W * H * 4,
+                    "d2h_bytes_per_step": count_all * W * H * 3,
                     "api": "ofxcv_inpaint_sequence_u8_host, page-locked host frames, uploads / downloads overlap the other frames' compute"},
             "gpu_launches": int(launches_all), "clocks": clocks, "checksums": sums,
         }
@@ -614,7 +620,8 @@ def run_watershed(args, wl):
     lab0 = d_mk.download((count, H, W), np.int32)[0] if rank == 0 and world == 1 else None
     step_e2e()
     ms_e2e = rig.timed(step_e2e, args.steps, blocking=True)
-    frames_all = rig.total(count) * args.steps
+    count_all = int(rig.total(count))   # every collective on every rank; below only rank 0 works
+    frames_all = count_all * args.steps
     launches_all = rig.total(launches)
     sums = checksum_report(rig, keys)
     if rank == 0:
@@ -625,7 +632,7 @@ def run_watershed(args, wl):
             "metric": wl["metric"], "value": frames_all / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i32", "data": "synthetic: Texture(seed 4) RGB8, %d 5x5 seed squares (seed 5), the same frame on every rank" % wl["seeds"],
-            "config": dict(workload_config(args.workload, wl, int(rig.total(count))), **{
+            "config": dict(workload_config(args.workload, wl, count_all), **{
                 "sharding": "one frame per GPU per step (frames of a sequence are independent)",
                 "call": "ofxcv_watershed_u8c3_batch with %d frame(s): the exact intra-frame parallel flood (watershed_par.cu), %d rounds / %d passes for this frame" % (
                     count, stats[2], stats[3]),
@@ -636,8 +643,8 @@ def run_watershed(args, wl):
                          "note": "an ordered flood is bound by the length of its dependency chains (the longest sub-flood of every round), "
                                  "not by HBM: the fraction is reported because the contract asks for it, it is not a target"},
             "pops_per_frame": int(stats[0] // max(count, 1)),
-            "e2e": {"value": frames_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(rig.total(count * W * H * 7)),
-                    "d2h_bytes_per_step": int(rig.total(count * W * H * 4)), "api": "ofxcv_watershed_u8c3_host, page-locked host frame and markers"},
+            "e2e": {"value": frames_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": count_all * W * H * 7,
+                    "d2h_bytes_per_step": count_all * W * H * 4, "api": "ofxcv_watershed_u8c3_host, page-locked host frame and markers"},
             "gpu_launches": int(launches_all), "clocks": clocks, "checksums": sums,
         }
         if world == 1 and lab0 is not None and not args.no_parity:
