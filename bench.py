@@ -394,6 +394,22 @@ def run_flow(args, wl):
     for _ in range(2):
         step_e2e()
     ms_e2e = rig.timed(step_e2e, args.steps)
+
+    # the ceiling the host fabric puts on e2e: the same H2D and D2H bytes, same page-locked buffers, NO compute, uploads on the
+    # library's stream and downloads on its staging stream (full duplex), all ranks at once
+    L = pkg.lib()
+    aux = L.ofxcv_aux_stream(ctx.h)
+
+    def step_copies():
+        for n in calls:
+            for t in range(n + 1):
+                L.ofxcv_upload(ctx.h, None, d_frames.ptr + t * W * H, h_frames[t].ctypes.data, W * H)
+            for t in range(n):
+                L.ofxcv_download(ctx.h, aux, h_flows[t].ctypes.data, d_flows.ptr + t * W * H * 8, W * H * 8)
+        L.ofxcv_stream_wait(ctx.h, None, aux)     # the timing events sit on the main stream
+
+    step_copies()
+    ms_copy = rig.timed(step_copies, args.steps)
     # every collective happens here, on every rank; below this point only rank 0 works
     count_all = int(rig.total(count))
     pairs_all = count_all * args.steps
@@ -440,7 +456,11 @@ def run_flow(args, wl):
                          "whole_pair_model": "per GPU: sum over calls of (n+1) frame pyramids x %.3f GB + n solves x %.3f GB (a stand-alone pair = %.3f GB)" % (
                              frame_bytes / 1e9, solve_bytes / 1e9, pair_model / 1e9)},
             "e2e": {"value": pairs_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
-                    "api": "ofxcv_farneback_sequence_u8_host, page-locked host frames, upload/compute/download on three streams"},
+                    "api": "ofxcv_farneback_sequence_u8_host, page-locked host frames, upload/compute/download on three streams",
+                    "copy_ceiling": {"value": pairs_all / (ms_copy * 1e-3), "unit": UNIT,
+                                     "gb_per_s_per_gpu": (h2d_all + d2h_all) / max(world, 1) * args.steps / (ms_copy * 1e-3) / 1e9,
+                                     "what": "the same H2D + D2H bytes from / to the same page-locked buffers with no compute, both directions at once, all ranks at once"},
+                    "frac_of_copy_ceiling": (pairs_all / (ms_e2e * 1e-3)) / (pairs_all / (ms_copy * 1e-3))},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "checksums": sums,
