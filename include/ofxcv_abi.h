@@ -12,9 +12,16 @@
  * Return value: 0 (OFXCV_OK) or a negative ofxcv_status.  There is NO CPU fallback anywhere in this library:
  * without a usable CUDA device `ofxcv_create` returns NULL and every op returns OFXCV_ERR_NO_DEVICE.
  *
- * Threading: a context is used by one thread at a time (it owns its workspace, stream and pinned staging);
- * create one per render thread (the OFX glue keeps a small pool).  Different contexts are fully independent,
- * so the library is re-entrant as kOfxImageEffectRenderFullySafe needs (VectorGenerator.cpp:108).
+ * Threading: a context is used by one thread at a time (it owns its workspace, streams and pinned staging);
+ * create one per render thread (the OFX glue keeps a pool per device).  Different contexts are fully independent,
+ * so the library is re-entrant as kOfxImageEffectRenderFullySafe needs (VectorGenerator.cpp:108).  Two families of
+ * calls start threads of their own inside the library and join them before returning: ofxcv_upload_rows /
+ * ofxcv_download_rows (row-copy workers) and ofxcv_inpaint_sequence_u8[_host] (one worker per frame in flight, each on
+ * a sub-context of `ctx`); a host with its own render threads needs no extra care, it only must not share one
+ * context between them.
+ * Blocking: the device flavours only enqueue work, with two exceptions that loop on the host and return when done:
+ * ofxcv_watershed_u8c3[_batch] with fewer than 16 frames (round loop of the parallel flood) and the inpaint calls
+ * (the marching reads its batch counters back).
  */
 #ifndef OFXCV_ABI_H
 #define OFXCV_ABI_H
@@ -148,11 +155,14 @@ OFXCV_API int ofxcv_farneback_u8_host(ofxcv_ctx* ctx, const uint8_t* prev, const
  * mean equal pixels, size and parameters); the context keeps the polynomial-expansion pyramids of the last few
  * keyed frames, so that frame t+1 of pair t is not blurred / expanded again as frame t of pair t+1 (or for the
  * backward flow of the same render: VectorGenerator.cpp:559-638 runs t->t+1 and t->t-1).  Calls that share keys
- * must be issued on the same stream.  key 0 = anonymous (what ofxcv_farneback_u8 passes). */
+ * may be issued on different streams (a hit waits for the event of the build).  The context keeps eight pyramids (least
+ * recently used replaced).  key 0 = anonymous (what ofxcv_farneback_u8 passes).  Returns OFXCV_ABORTED (1) when the
+ * abort callback fired between two pyramid scales. */
 OFXCV_API int ofxcv_farneback_u8_keyed(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* prev, const uint8_t* next,
                                        ptrdiff_t stride, int W, int H, float* flow, ptrdiff_t flow_stride,
                                        const ofxcv_fb_params* params, uint64_t key_prev, uint64_t key_next);
-/* a content key for the call above: 64-bit position-sensitive hash of a device-resident 8-bit plane (never 0).
+/* a content key for the call above: position-sensitive hash of a device-resident 8-bit plane (two independent 64-bit
+ * lanes folded together with the geometry; never 0).
  * Synchronises `stream`.  The VectorGenerator glue keys every staged gray frame with it, so that consecutive
  * renders of a clip (and the forward / backward flow of one render) share frame pyramids. */
 OFXCV_API int ofxcv_content_key_u8(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* img, ptrdiff_t stride, int W,
@@ -253,7 +263,11 @@ OFXCV_API int ofxcv_inpaint_debug_maps(ofxcv_ctx* ctx, int W, int H, float* t_ho
 /* ---- segmentation ----------------------------------------------------------------------------------- */
 /* Replaces the segment plugin's body (cvPyrSegmentation at /root/reference/opencv2fx/segment/segment.cpp:296-302)
  * by cv::watershed(rgb8, int32 markers) as BASELINE.json config 3 requires.
- * rgb: 3-channel interleaved u8; markers: int32 in/out (>0 seeds; on return labels >0, -1 ridges + border). */
+ * rgb: 3-channel interleaved u8; markers: int32 in/out (>0 seeds; on return labels >0, -1 ridges + border).
+ * The label map is the one of OpenCV's sequential Meyer flood, bit for bit, by two exact schedules: fewer than 16 frames
+ * are flooded one after the other by the intra-frame PARALLEL flood (rounds of speculative blocks ordered by rank,
+ * csrc/watershed_par.cu: a 4K frame in ~0.3 s, blocking call), 16 or more by one thread per frame with all frames in
+ * flight (asynchronous).  OFXCV_WS_MODE=par|seq forces one of them. */
 OFXCV_API int ofxcv_watershed_u8c3(ofxcv_ctx* ctx, ofxcv_stream stream, const uint8_t* rgb, ptrdiff_t rgb_stride,
                                    int32_t* markers, ptrdiff_t markers_stride, int W, int H);
 OFXCV_API int ofxcv_watershed_u8c3_host(ofxcv_ctx* ctx, const uint8_t* rgb, ptrdiff_t rgb_stride, int32_t* markers,
@@ -265,7 +279,8 @@ OFXCV_API int ofxcv_watershed_u8c3_batch(ofxcv_ctx* ctx, ofxcv_stream stream, co
                                          ptrdiff_t markers_stride, size_t markers_frame_stride, int W, int H,
                                          int nframes);
 OFXCV_API size_t ofxcv_watershed_workspace_bytes(int W, int H, int nframes);
-/* stats of the last call: [0]=queue pops (all frames) */
+/* stats of the last call: [0]=queue pops (all frames), [1]=frames, [2]=rounds and [3]=passes of the parallel flood
+ * (last frame; 0 when the one-thread flood ran) */
 OFXCV_API int ofxcv_watershed_last_stats(const ofxcv_ctx* ctx, int64_t stats[4]);
 
 /* ---- staging conversions (the steps either side of the OpenCV call inside the render actions) ------- */
