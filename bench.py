@@ -323,7 +323,7 @@ def checksum_report(rig, keys):
     longest = max(allk, key=len)
     same = all(k == longest[:len(k)] for k in allk)
     return {"identical_across_ranks": bool(same), "ranks": len(allk), "outputs_compared": min(len(k) for k in allk),
-            "digest_first_block": digest(longest), "how": "ofxcv_content_key_u8 over the bytes of every output of the rank's first call"}
+            "digest_first_block": digest(longest), "key_output_0": "%016x" % longest[0] if longest else None, "how": "ofxcv_content_key_u8 over the bytes of every output of the rank's first call"}
 
 
 def cpu_baseline_leg(args, line):
@@ -377,7 +377,9 @@ def run_flow(args, wl):
     launches = ctx.launch_count() - l0
     n_iter_situ, iter_ms_situ = ctx.kernel_time_ms(0)   # with the other lanes' kernels sharing the GPU
     clocks = sampler.stop() if sampler else None
-    keys = [ctx.content_key(d_flows.ptr + i * W * H * 8, W * 8, H) for i in range(calls[-1])] if calls else []
+    # every call of a step writes the same block of flow fields (periodic sequence), so after the step slot i holds pair i of
+    # the block whichever call wrote it last: the keys cover one full call and do not depend on how many ranks share the clip
+    keys = [ctx.content_key(d_flows.ptr + i * W * H * 8, W * 8, H) for i in range(max(calls))] if calls else []
     flow0 = d_flows.download((1, H, W, 2), np.float32)[0] if (rank == 0 and world == 1 and calls[-1] >= 1) else None
     # the same K steps without the per-kernel events, to show what the instrumentation costs
     ms_plain = rig.timed(step_resident, args.steps)
