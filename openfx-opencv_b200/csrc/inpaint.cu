@@ -1121,6 +1121,355 @@ ip_fill_staged(const uint32_t* __restrict__ order, unsigned nfill, const int32_t
     }
 }
 
+// ---- Stage B, incremental: the chain step shrunk to "the taps the last dependency touches" ---------------------------
+// ip_fill_staged (in-order tickets) waits for ALL earlier-filled pixels of the box and only then evaluates its 49-81 taps:
+// the chain step is poll + every tap + the ordered sum (~6200 cycles after the wait at radius 3).  But a pending pixel p
+// only enters the taps at p and at its neighbours (a tap reads its own colour and the colours of its 4-neighbours, clamped
+// at the image border: all inside the 3x3 around it).  Here a warp
+//   * stages everything that is there at first look and keeps a warp-uniform bit mask P of the box positions still pending,
+//   * evaluates -- compacted over the lanes, one tap per lane -- every tap whose 3x3 neighbourhood has nothing pending,
+//     writes its terms to a per-tap table in shared memory, then polls the pending words; whenever some arrive, the taps
+//     they release are evaluated the same way (usually a handful: one short round),
+//   * and when nothing is pending sums the table in the CPU's tap order (one lane per accumulator) as before.
+// So what follows the arrival of the LAST dependency is one round over <= 9 taps + the ordered sum + the publication.
+// Same arithmetic, same expression forms, same order of the accumulator sums as ip_fill / ip_fill_staged.
+// Used with the in-order scheduler for radius <= 4 (tabulated geometry); OFXCV_IP_FILL_INC=0 selects ip_fill_staged.
+template <int METHOD, int CN, int MINB>
+__global__ void __launch_bounds__(IP_WARPS * 32, MINB)
+ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __restrict__ fidx, const float* __restrict__ t,
+            uint8_t* out, ptrdiff_t ostride, unsigned* __restrict__ ticket, uint32_t* pub, int range, IpGeom g)
+{
+    constexpr int NACC = METHOD == OFXCV_INPAINT_TELEA ? 4 * CN : 2 * CN;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char ip3_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int ec = g.ec, er = g.er;
+    const int side = 2 * range + 1, ntaps = side * side;
+    const int bside = 2 * range + 3, nbox = bside * bside;
+    const int nbox_pad = (nbox + 3) & ~3;
+    const int nrounds = (ntaps + 31) >> 5;  // <= IP2_NTAP
+    // CTA: the 3x3 "affected by" masks of every tap (4 words over the box positions); per warp: packed colour+known word
+    // and T of every box position, the term table [tap][accumulator], the compaction list
+    uint4* s_aff = reinterpret_cast<uint4*>(ip3_smem);
+    const size_t per_warp = (size_t)nbox_pad * 8 + (size_t)nrounds * 32 * (IP_MAXACC + 1) * 4 + (size_t)nrounds * 32 * 4;
+    unsigned char* wbase = ip3_smem + (size_t)2 * IP2_NTAP * 32 * 16 + per_warp * wid;
+    uint32_t* s_px = reinterpret_cast<uint32_t*>(wbase);
+    float* s_t = reinterpret_cast<float*>(s_px + nbox_pad);
+    float(*s_term)[IP_MAXACC + 1] = reinterpret_cast<float(*)[IP_MAXACC + 1]>(s_t + nbox_pad);
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_term + nrounds * 32);
+
+    // geometry of this lane's box positions and taps: the same for every pixel
+    int pk[IP2_NPOS], pl[IP2_NPOS];  // box position -> offset from the box origin (row, col); row < 0 = none
+#pragma unroll
+    for (int q = 0; q < IP2_NPOS; q++) {
+        const int b = q * 32 + lane;
+        pk[q] = b < nbox ? b / bside : -1;
+        pl[q] = b < nbox ? b - (b / bside) * bside : 0;
+    }
+    int tdk[IP2_NTAP], tdl[IP2_NTAP];  // tap -> offset from the pixel; tdk = -2^20 = no tap / outside the disc
+#pragma unroll
+    for (int u = 0; u < IP2_NTAP; u++) {
+        const int tp = u * 32 + lane;
+        const int dk = tp / side - range, dl = tp % side - range;
+        const bool in = tp < ntaps && dk * dk + dl * dl <= range * range;
+        tdk[u] = in ? dk : -(1 << 20);
+        tdl[u] = dl;
+    }
+    // table 0: the tap and its 4-neighbours (what a tap away from the image border reads); table 1: the whole 3x3 (the
+    // clamped indices of a tap on the border ring stay inside it)
+    for (int e = threadIdx.x; e < 2 * IP2_NTAP * 32; e += blockDim.x) {
+        const int tp = e % (IP2_NTAP * 32), full3 = e / (IP2_NTAP * 32);
+        unsigned m[4] = {0u, 0u, 0u, 0u};
+        if (tp < ntaps) {
+            const int x = (tp / side + 1) * bside + (tp % side + 1);  // box index of the tap
+            for (int dr = -1; dr <= 1; dr++)
+                for (int dc = -1; dc <= 1; dc++) {
+                    if (!full3 && dr != 0 && dc != 0) continue;
+                    const int p = x + dr * bside + dc;
+#pragma unroll
+                    for (int w = 0; w < 4; w++)
+                        if ((p >> 5) == w) m[w] |= 1u << (p & 31);
+                }
+        }
+        s_aff[e] = make_uint4(m[0], m[1], m[2], m[3]);
+    }
+    __syncthreads();
+
+    for (;;) {
+        unsigned tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1u);
+        tk = __shfl_sync(FULL, tk, 0);
+        if (tk >= nfill) break;
+        const int id = (int)order[tk];
+        const int i = id / ec, j = id - i * ec;
+        const int k0 = i - range - 1, l0 = j - range - 1;  // map coordinates of box position (0, 0)
+
+        // first look: fill index of every box position, colours of what is not a dependency, T, the published words of
+        // the dependencies
+        int fi[IP2_NPOS];
+        bool pend[IP2_NPOS];
+        uint32_t px[IP2_NPOS];
+        float tv[IP2_NPOS];
+#pragma unroll
+        for (int q = 0; q < IP2_NPOS; q++) {
+            fi[q] = -1;
+            if (pk[q] >= 0) {
+                const int k = k0 + pk[q], l = l0 + pl[q];
+                if (k >= 0 && l >= 0 && k < er && l < ec) fi[q] = __ldg(fidx + k * ec + l);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < IP2_NPOS; q++) {
+            px[q] = 0;
+            tv[q] = 0.f;
+            pend[q] = false;
+            if (pk[q] >= 0) {
+                const int k = k0 + pk[q], l = l0 + pl[q];
+                const bool dep = fi[q] >= 0 && fi[q] < (int)tk;
+                if (dep) {
+                    const uint32_t v = *((volatile uint32_t*)pub + fi[q]);
+                    pend[q] = (v >> 31) == 0;
+                    px[q] = v & 0x00ffffffu;
+                } else if (k >= 1 && l >= 1 && k <= g.H && l <= g.W) {
+                    const uint8_t* o = out + (size_t)(k - 1) * ostride + (size_t)(l - 1) * CN;
+#pragma unroll
+                    for (int c = 0; c < CN; c++) px[q] |= (uint32_t)ld_u8_cg(o + c) << (8 * c);
+                }
+                if (METHOD == OFXCV_INPAINT_TELEA && k >= 0 && l >= 0 && k < er && l < ec) tv[q] = __ldg(t + k * ec + l);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < IP2_NPOS; q++)
+            if (pk[q] >= 0) {
+                s_px[q * 32 + lane] = ((fi[q] < (int)tk ? 1u : 0u) << 24) | (pend[q] ? 0u : px[q]);
+                s_t[q * 32 + lane] = tv[q];
+            }
+        __syncwarp();
+
+        // box accessors: map position (k, l) / image position (r, c) = map (r+1, c+1)
+        auto bidx = [&](int k, int l) -> int { return (k - k0) * bside + (l - l0); };
+        auto known = [&](int k, int l) -> bool { return (s_px[bidx(k, l)] >> 24) != 0; };
+#define OUTP(r, c, ch) (int)((s_px[bidx((r) + 1, (c) + 1)] >> (8 * (ch))) & 0xffu)
+#define TV(k, l) s_t[bidx((k), (l))]
+
+        float gTx = 0.f, gTy = 0.f, ti = 0.f;
+        if (METHOD == OFXCV_INPAINT_TELEA) {  // the known flags and T never wait for anybody
+            ti = TV(i, j);
+            if (known(i, j + 1)) {
+                if (known(i, j - 1)) gTx = (float)(TV(i, j + 1) - TV(i, j - 1)) * 0.5f;
+                else gTx = (float)(TV(i, j + 1) - ti);
+            } else {
+                if (known(i, j - 1)) gTx = (float)(ti - TV(i, j - 1));
+                else gTx = 0;
+            }
+            if (known(i + 1, j)) {
+                if (known(i - 1, j)) gTy = (float)(TV(i + 1, j) - TV(i - 1, j)) * 0.5f;
+                else gTy = (float)(TV(i + 1, j) - ti);
+            } else {
+                if (known(i - 1, j)) gTy = (float)(ti - TV(i - 1, j));
+                else gTy = 0;
+            }
+        }
+
+        // the taps that contribute (known, inside the disc, not on the map's border ring) and their masks in tap order
+        bool todo[IP2_NTAP];
+        unsigned vm[IP2_NTAP];
+#pragma unroll
+        for (int u = 0; u < IP2_NTAP; u++) {
+            todo[u] = false;
+            if (u < nrounds && tdk[u] > -(1 << 19)) {
+                const int k = i + tdk[u], l = j + tdl[u];
+                todo[u] = k > 0 && l > 0 && k < er - 1 && l < ec - 1 && known(k, l);
+            }
+            vm[u] = __ballot_sync(FULL, todo[u]);
+        }
+        // Only a pending pixel that one of these taps reads can hold this pixel up: the box corners, the positions around
+        // taps that are themselves unknown ... are struck from the wait list (this alone cuts the dependency chain of an
+        // iid 10 % mask at 4K from ~2700 to ~900 steps).  P = the pending positions that matter, one word per 32 positions.
+        const bool interior = i - range >= 2 && i + range <= g.H - 1 && j - range >= 2 && j + range <= g.W - 1;
+        const uint4* aff = s_aff + (interior ? 0 : IP2_NTAP * 32);
+        unsigned P[IP2_NPOS];
+        {
+            unsigned rel[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int u = 0; u < IP2_NTAP; u++)
+                if (todo[u]) {
+                    const uint4 a = aff[u * 32 + lane];
+                    rel[0] |= a.x; rel[1] |= a.y; rel[2] |= a.z; rel[3] |= a.w;
+                }
+#pragma unroll
+            for (int q = 0; q < IP2_NPOS; q++) {
+                const unsigned r = __reduce_or_sync(FULL, rel[q]);
+                pend[q] = pend[q] && ((r >> lane) & 1u);
+                P[q] = __ballot_sync(FULL, pend[q]);
+            }
+        }
+
+        for (;;) {
+            // hand every tap with nothing pending around it to a lane
+            int total = 0;
+#pragma unroll
+            for (int u = 0; u < IP2_NTAP; u++) {
+                bool r = false;
+                if (todo[u]) {
+                    const uint4 a = aff[u * 32 + lane];
+                    r = ((a.x & P[0]) | (a.y & P[1]) | (a.z & P[2]) | (a.w & P[3])) == 0u;
+                }
+                const unsigned m = __ballot_sync(FULL, r);
+                if (r) {
+                    s_list[total + __popc(m & lt)] = (uint32_t)(u * 32 + lane) | ((uint32_t)(tdk[u] + 64) << 8) | ((uint32_t)(tdl[u] + 64) << 16);
+                    todo[u] = false;
+                }
+                total += __popc(m);
+            }
+            __syncwarp();
+            for (int base = 0; base < total; base += 32) {
+                if (base + lane < total) {
+                    const uint32_t e = s_list[base + lane];
+                    const int tp = (int)(e & 0xffu), dk = (int)((e >> 8) & 0xffu) - 64, dl = (int)((e >> 16) & 0xffu) - 64;
+                    const int k = i + dk, l = j + dl;
+                    float term[IP_MAXACC];
+                    const int km = k - 1 + (k == 1), kp = k - 1 - (k == er - 2);
+                    const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ec - 2);
+                    const bool fr = known(k, l + 1), fl = known(k, l - 1), fd = known(k + 1, l), fu = known(k - 1, l);
+                    if (METHOD == OFXCV_INPAINT_TELEA) {
+                        float ry = (float)(i - k), rx = (float)(j - l);
+                        float vl = rx * rx + ry * ry;
+                        float dst = (float)(1. / (vl * sqrt((double)vl)));
+                        float lev = (float)(1. / (1 + (double)fabsf(TV(k, l) - ti)));  // f32 difference, f64 sum (C fabs)
+                        float dir = rx * gTx + ry * gTy;
+                        if (fabs(dir) <= 0.01) dir = 0.000001f;
+                        float w = (float)fabs(dst * lev * dir);
+#pragma unroll
+                        for (int c = 0; c < CN; c++) {
+                            float gIx, gIy;
+                            if (fr) {
+                                if (fl) gIx = (float)(OUTP(km, lp + 1, c) - OUTP(km, lm - 1, c)) * 2.0f;
+                                else gIx = (float)(OUTP(km, lp + 1, c) - OUTP(km, lm, c));
+                            } else {
+                                if (fl) gIx = (float)(OUTP(km, lp, c) - OUTP(km, lm - 1, c));
+                                else gIx = 0;
+                            }
+                            if (fd) {
+                                if (fu) gIy = (float)(OUTP(kp + 1, lm, c) - OUTP(km - 1, lm, c)) * 2.0f;
+                                else gIy = (float)(OUTP(kp + 1, lm, c) - OUTP(km, lm, c));
+                            } else {
+                                if (fu) gIy = (float)(OUTP(kp, lm, c) - OUTP(km - 1, lm, c));
+                                else gIy = 0;
+                            }
+                            term[c * 4 + 0] = w * (float)OUTP(k - 1, l - 1, c);
+                            term[c * 4 + 1] = -(w * (gIx * rx));
+                            term[c * 4 + 2] = -(w * (gIy * ry));
+                            term[c * 4 + 3] = w;
+                        }
+                    } else {
+                        float ry = (float)(k - i), rx = (float)(l - j);
+                        float vl = rx * rx + ry * ry;
+                        float dst = 1 / (vl * vl + 1);
+#pragma unroll
+                        for (int c = 0; c < CN; c++) {
+                            float gIx, gIy;
+                            if (fd) {
+                                if (fu) gIx = (float)(abs(OUTP(kp + 1, lm, c) - OUTP(kp, lm, c)) + abs(OUTP(kp, lm, c) - OUTP(km - 1, lm, c)));
+                                else gIx = (float)(abs(OUTP(kp + 1, lm, c) - OUTP(kp, lm, c))) * 2.0f;
+                            } else {
+                                if (fu) gIx = (float)(abs(OUTP(kp, lm, c) - OUTP(km - 1, lm, c))) * 2.0f;
+                                else gIx = 0;
+                            }
+                            if (fr) {
+                                if (fl) gIy = (float)(abs(OUTP(km, lp + 1, c) - OUTP(km, lm, c)) + abs(OUTP(km, lm, c) - OUTP(km, lm - 1, c)));
+                                else gIy = (float)(abs(OUTP(km, lp + 1, c) - OUTP(km, lm, c))) * 2.0f;
+                            } else {
+                                if (fl) gIy = (float)(abs(OUTP(km, lm, c) - OUTP(km, lm - 1, c))) * 2.0f;
+                                else gIy = 0;
+                            }
+                            gIx = -gIx;
+                            float dir = rx * gIx + ry * gIy;
+                            if (fabs(dir) <= 0.01) dir = 0.000001f;
+                            else dir = fabsf((rx * gIx + ry * gIy) / sqrtf(vl * (gIx * gIx + gIy * gIy)));
+                            float w = dst * dir;
+                            term[c * 2 + 0] = w * (float)OUTP(k - 1, l - 1, c);
+                            term[c * 2 + 1] = w;
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < NACC; a++) s_term[tp][a] = term[a];
+                }
+            }
+            __syncwarp();
+            if ((P[0] | P[1] | P[2] | P[3]) == 0u) break;  // nothing was pending: that round was the last
+            // poll the pending words until some have arrived, stage them, release the taps around them
+            uint32_t pv[IP2_NPOS];
+            bool got;
+            do {
+                got = false;
+#pragma unroll
+                for (int q = 0; q < IP2_NPOS; q++) {
+                    pv[q] = 0;
+                    if (pend[q]) pv[q] = *((volatile uint32_t*)pub + fi[q]);
+                    got |= (pv[q] >> 31) != 0;
+                }
+            } while (!__any_sync(FULL, got));
+#pragma unroll
+            for (int q = 0; q < IP2_NPOS; q++) {
+                if (pend[q] && (pv[q] >> 31)) {
+                    s_px[q * 32 + lane] = (1u << 24) | (pv[q] & 0x00ffffffu);
+                    pend[q] = false;
+                }
+                P[q] = __ballot_sync(FULL, pend[q]);
+            }
+            __syncwarp();
+        }
+#undef OUTP
+#undef TV
+
+        // the accumulators, summed in tap order: lane a < NACC owns accumulator a
+        float acc = 0.f;
+        if (METHOD == OFXCV_INPAINT_TELEA) { if ((lane & 3) == 3) acc = 1.0e-20f; }
+        else { if ((lane & 1) == 1) acc = 1.0e-20f; }
+        if (lane < NACC) {
+#pragma unroll
+            for (int u = 0; u < IP2_NTAP; u++)
+                if (u < nrounds) {
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 32; q++) v[q] = s_term[u * 32 + q][lane];
+#pragma unroll
+                    for (int q = 0; q < 32; q++)
+                        if ((vm[u] >> q) & 1u) acc = acc + v[q];
+                }
+        }
+        __syncwarp();
+
+        // finish: lane c gathers its channel's accumulators
+        uint8_t result = 0;
+        if (METHOD == OFXCV_INPAINT_TELEA) {
+            int c = lane < CN ? lane : 0;
+            float Ia = __shfl_sync(FULL, acc, c * 4 + 0);
+            float Jx = __shfl_sync(FULL, acc, c * 4 + 1);
+            float Jy = __shfl_sync(FULL, acc, c * 4 + 2);
+            float s = __shfl_sync(FULL, acc, c * 4 + 3);
+            float sat = Ia / s + (Jx + Jy) / (sqrtf(Jx * Jx + Jy * Jy) + 1.0e-20f) + 0.5f;
+            int iv = __double2int_rn((double)sat);
+            result = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+        } else {
+            int c = lane < CN ? lane : 0;
+            float Ia = __shfl_sync(FULL, acc, c * 2 + 0);
+            float s = __shfl_sync(FULL, acc, c * 2 + 1);
+            int iv = __double2int_rn((double)Ia / s);
+            result = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+        }
+        // colour + done bit in one word: what the dependents poll
+        uint32_t word = 0x80000000u;
+#pragma unroll
+        for (int c = 0; c < CN; c++) word |= (uint32_t)__shfl_sync(FULL, (unsigned)result, c) << (8 * c);
+        if (lane == 0) *((volatile uint32_t*)pub + tk) = word;
+        if (lane < CN) out[(size_t)(i - 1) * ostride + (size_t)(j - 1) * CN + lane] = result;
+        __syncwarp();
+    }
+}
+
 // dependency counts of the ready-queue fill: dep[tk] = number of earlier-filled hole pixels in the (2r+3)^2 box of the
 // pixel with fill index tk; pixels without any go straight into the ready queue
 // Also counts the pixels whose latest dependency is one of the 64 tickets right before them (`near`): when that is most
@@ -1336,9 +1685,25 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
         }
         const int nbox_pad = ((2 * range + 3) * (2 * range + 3) + 3) & ~3;
         const size_t fill_smem = v2 ? ((size_t)nbox_pad * 8 + 32 * (IP_MAXACC + 1) * 4) * IP_WARPS : 0;
+        // incremental fill (ip_fill_inc): in-order scheduler, tabulated geometry (radius <= 4)
+        const int ntaps = (2 * range + 1) * (2 * range + 1), nrounds = (ntaps + 31) / 32;
+        static const int inc_env = getenv("OFXCV_IP_FILL_INC") ? atoi(getenv("OFXCV_IP_FILL_INC")) : 1;
+        const bool inc = v2 && !ready_queue && inc_env != 0 && nbox_pad <= 32 * IP2_NPOS && ntaps <= 32 * IP2_NTAP;
+        const size_t inc_smem = (size_t)2 * IP2_NTAP * 32 * 16 +
+                                ((size_t)nbox_pad * 8 + (size_t)nrounds * 32 * (IP_MAXACC + 1) * 4 + (size_t)nrounds * 32 * 4) * IP_WARPS;
+#define IP_FILL_INC(M, C, B)                                                                                                       \
+    do {                                                                                                                           \
+        if (inc_smem > 48 * 1024)                                                                                                  \
+            OFXCV_CUDA(ctx, cudaFuncSetAttribute(ip_fill_inc<M, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inc_smem)); \
+        ip_fill_inc<M, C, B><<<blocks, IP_WARPS * 32, inc_smem, s>>>(order, nfilled, fidx, t, out, out_stride, &ctr->ticket, pub,  \
+                                                                     range, g);                                                    \
+    } while (0)
 #define IP_FILL(M, C)                                                                                                              \
     do {                                                                                                                           \
-        if (v2) {                                                                                                                  \
+        if (inc) {                                                                                                                 \
+            if (inc_env == 3) IP_FILL_INC(M, C, 3);                                                                                \
+            else IP_FILL_INC(M, C, 4);                                                                                             \
+        } else if (v2) {                                                                                                              \
             if (fill_smem > 48 * 1024) {                                                                                           \
                 OFXCV_CUDA(ctx, cudaFuncSetAttribute(ip_fill_staged<M, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                                      (int)fill_smem));                                                             \
@@ -1366,6 +1731,7 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
             else IP_FILL(OFXCV_INPAINT_NS, 1);
         }
 #undef IP_FILL
+#undef IP_FILL_INC
         ofxcv_time_end(ctx, 1, s);
         OFXCV_LAUNCH_CHECK(ctx);
     }
