@@ -1121,23 +1121,48 @@ ip_fill_staged(const uint32_t* __restrict__ order, unsigned nfill, const int32_t
     }
 }
 
-// ---- Stage B, incremental: the chain step shrunk to "the taps the last dependency touches" ---------------------------
-// ip_fill_staged (in-order tickets) waits for ALL earlier-filled pixels of the box and only then evaluates its 49-81 taps:
-// the chain step is poll + every tap + the ordered sum (~6200 cycles after the wait at radius 3).  But a pending pixel p
-// only enters the taps at p and at its neighbours (a tap reads its own colour and the colours of its 4-neighbours, clamped
-// at the image border: all inside the 3x3 around it).  Here a warp
-//   * stages everything that is there at first look and keeps a warp-uniform bit mask P of the box positions still pending,
-//   * evaluates -- compacted over the lanes, one tap per lane -- every tap whose 3x3 neighbourhood has nothing pending,
-//     writes its terms to a per-tap table in shared memory, then polls the pending words; whenever some arrive, the taps
-//     they release are evaluated the same way (usually a handful: one short round),
-//   * and when nothing is pending sums the table in the CPU's tap order (one lane per accumulator) as before.
-// So what follows the arrival of the LAST dependency is one round over <= 9 taps + the ordered sum + the publication.
-// Same arithmetic, same expression forms, same order of the accumulator sums as ip_fill / ip_fill_staged.
-// Used with the in-order scheduler for radius <= 4 (tabulated geometry); OFXCV_IP_FILL_INC=0 selects ip_fill_staged.
+// source colour of every hole pixel by fill index (packed like the published words), taken before the fill starts
+template <int CN>
+__global__ void __launch_bounds__(256) ip_orig(const uint32_t* __restrict__ order, unsigned nfill, const uint8_t* __restrict__ out,
+                                               ptrdiff_t ostride, uint32_t* __restrict__ orig, IpGeom g)
+{
+    const unsigned tk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tk >= nfill) return;
+    const int id = (int)order[tk];
+    const int i = id / g.ec, j = id - i * g.ec;
+    const uint8_t* o = out + (size_t)(i - 1) * ostride + (size_t)(j - 1) * CN;
+    uint32_t v = 0;
+#pragma unroll
+    for (int c = 0; c < CN; c++) v |= (uint32_t)o[c] << (8 * c);
+    orig[tk] = v;
+}
+
+// ---- Stage B, incremental (the default for radius <= 4 with the in-order scheduler) ----------------------------------
+// ip_fill_staged waits for ALL earlier-filled pixels of the (2r+3)^2 box and only then evaluates its 49-81 taps: the chain
+// step is poll + every tap + the ordered sum (~6200 cycles after the wait at radius 3), and the chain of an iid 10 % mask at
+// 4K is ~2700 steps deep.  Two observations shorten both factors:
+//   1. A pending pixel p only enters the taps at p and at p's 4-neighbours (a tap reads its own colour and those of its
+//      4-neighbours; on the image's border ring the CPU code's clamped indices stay inside the 3x3 around the tap).  So the
+//      only pending pixels that can hold a pixel up are those around a tap that CONTRIBUTES (inside the disc, known): the box
+//      corners, the positions around unknown taps ... are struck from the wait list.  That alone cuts the chain of the iid
+//      mask from ~2700 to ~900 steps (tools measured it on the CPU from the oracle's fill order) and the fill from 11.7 to
+//      5.9 ms.
+//   2. Everything that does not touch a pending pixel can be evaluated BEFORE the wait.  A warp stages what is there at first
+//      look, keeps a warp-uniform bit mask P of the (relevant) box positions still pending, evaluates -- compacted over the
+//      lanes, one tap per lane -- every tap with nothing pending around it into a per-tap term table in shared memory, THEN
+//      spins on the pending words, and evaluates the taps they held back in one more round (wait_all = 1, the default; with
+//      wait_all = 0 the taps are released arrival by arrival, which costs a pass over the tap arithmetic per arrival for
+//      the same critical path: measured equal).  The accumulators are then summed from the table in the CPU's tap order,
+//      one lane per accumulator, as before.  What follows the LAST arrival is one round over a few taps + the ordered sum +
+//      the publication instead of all of it: 5.9 -> 4.9 ms (NS), 4.4 ms (Telea); NS 81 -> 182 frames/s, Telea 75 -> 140 at 4K.
+// Same arithmetic, same expression forms, same order of the accumulator sums as ip_fill / ip_fill_staged: bit-identical.
+// Three resident CTAs per SM (80 registers): four (64 registers, spills) measured 20 % slower, two the same.
+// OFXCV_IP_FILL_INC=0 selects ip_fill_staged, OFXCV_IP_FILL_WAITALL=0 the arrival-by-arrival release.
 template <int METHOD, int CN, int MINB>
 __global__ void __launch_bounds__(IP_WARPS * 32, MINB)
 ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __restrict__ fidx, const float* __restrict__ t,
-            uint8_t* out, ptrdiff_t ostride, unsigned* __restrict__ ticket, uint32_t* pub, int range, IpGeom g)
+            uint8_t* out, ptrdiff_t ostride, unsigned* __restrict__ ticket, uint32_t* pub, const uint32_t* __restrict__ orig, int range,
+            int wait_all, IpGeom g)
 {
     constexpr int NACC = METHOD == OFXCV_INPAINT_TELEA ? 4 * CN : 2 * CN;
     constexpr unsigned FULL = 0xffffffffu;
@@ -1231,6 +1256,11 @@ ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* _
                     const uint32_t v = *((volatile uint32_t*)pub + fi[q]);
                     pend[q] = (v >> 31) == 0;
                     px[q] = v & 0x00ffffffu;
+                } else if (fi[q] > (int)tk && fi[q] != 0x7fffffff) {
+                    // a hole pixel filled LATER: not known, but a tap on the image's border ring reads neighbours whose flags it
+                    // did not test (the clamped indices of the CPU code).  What the CPU sees there at this pixel's time is the
+                    // source colour; `out` may already hold the colour a warp running ahead has written.
+                    px[q] = __ldg(orig + fi[q]);
                 } else if (k >= 1 && l >= 1 && k <= g.H && l <= g.W) {
                     const uint8_t* o = out + (size_t)(k - 1) * ostride + (size_t)(l - 1) * CN;
 #pragma unroll
@@ -1306,6 +1336,23 @@ ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* _
             }
         }
 
+        // spin until every pending word of this lane (and of the warp) has arrived, staging the colours
+        auto spin_all = [&](bool left) {
+            while (__any_sync(FULL, left)) {
+                left = false;
+#pragma unroll
+                for (int q = 0; q < IP2_NPOS; q++)
+                    if (pend[q]) {
+                        const uint32_t v = *((volatile uint32_t*)pub + fi[q]);
+                        if (v >> 31) {
+                            s_px[q * 32 + lane] = (1u << 24) | (v & 0x00ffffffu);
+                            pend[q] = false;
+                        } else {
+                            left = true;
+                        }
+                    }
+            }
+        };
         for (;;) {
             // hand every tap with nothing pending around it to a lane
             int total = 0;
@@ -1411,14 +1458,20 @@ ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* _
                     got |= (pv[q] >> 31) != 0;
                 }
             } while (!__any_sync(FULL, got));
+            bool left = false;
 #pragma unroll
             for (int q = 0; q < IP2_NPOS; q++) {
                 if (pend[q] && (pv[q] >> 31)) {
                     s_px[q * 32 + lane] = (1u << 24) | (pv[q] & 0x00ffffffu);
                     pend[q] = false;
                 }
-                P[q] = __ballot_sync(FULL, pend[q]);
+                left |= pend[q];
             }
+            // one more round only: every evaluation round costs the whole warp a pass over the tap arithmetic whatever the
+            // number of taps in it, and the round after the LAST arrival is as long with 29 taps as with 3
+            if (wait_all) spin_all(left);
+#pragma unroll
+            for (int q = 0; q < IP2_NPOS; q++) P[q] = __ballot_sync(FULL, pend[q]);
             __syncwarp();
         }
 #undef OUTP
@@ -1670,6 +1723,7 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
         int32_t* dep = (int32_t*)keys;  // the sort buffers are free once the march is over
         int32_t* rq = dep + np;
         uint32_t* pub = (uint32_t*)(rq + np);  // colour + done word per fill index (in-order scheduler)
+        uint32_t* orig = pub + np;             // source colour per fill index (ip_fill_inc)
         OFXCV_CUDA(ctx, cudaMemsetAsync(pub, 0, (size_t)nfilled * 4, s));
         bool ready_queue = false;
         if (v2) {
@@ -1688,6 +1742,7 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
         // incremental fill (ip_fill_inc): in-order scheduler, tabulated geometry (radius <= 4)
         const int ntaps = (2 * range + 1) * (2 * range + 1), nrounds = (ntaps + 31) / 32;
         static const int inc_env = getenv("OFXCV_IP_FILL_INC") ? atoi(getenv("OFXCV_IP_FILL_INC")) : 1;
+        static const int inc_wait_all = getenv("OFXCV_IP_FILL_WAITALL") ? atoi(getenv("OFXCV_IP_FILL_WAITALL")) : 1;
         const bool inc = v2 && !ready_queue && inc_env != 0 && nbox_pad <= 32 * IP2_NPOS && ntaps <= 32 * IP2_NTAP;
         const size_t inc_smem = (size_t)2 * IP2_NTAP * 32 * 16 +
                                 ((size_t)nbox_pad * 8 + (size_t)nrounds * 32 * (IP_MAXACC + 1) * 4 + (size_t)nrounds * 32 * 4) * IP_WARPS;
@@ -1695,14 +1750,14 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
     do {                                                                                                                           \
         if (inc_smem > 48 * 1024)                                                                                                  \
             OFXCV_CUDA(ctx, cudaFuncSetAttribute(ip_fill_inc<M, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inc_smem)); \
+        ip_orig<C><<<ofxcv_div_up((int)nfilled, 256), 256, 0, s>>>(order, nfilled, out, out_stride, orig, g);                      \
         ip_fill_inc<M, C, B><<<blocks, IP_WARPS * 32, inc_smem, s>>>(order, nfilled, fidx, t, out, out_stride, &ctr->ticket, pub,  \
-                                                                     range, g);                                                    \
+                                                                     orig, range, inc_wait_all, g);                                \
     } while (0)
 #define IP_FILL(M, C)                                                                                                              \
     do {                                                                                                                           \
         if (inc) {                                                                                                                 \
-            if (inc_env == 3) IP_FILL_INC(M, C, 3);                                                                                \
-            else IP_FILL_INC(M, C, 4);                                                                                             \
+            IP_FILL_INC(M, C, 3);                                                                                                  \
         } else if (v2) {                                                                                                              \
             if (fill_smem > 48 * 1024) {                                                                                           \
                 OFXCV_CUDA(ctx, cudaFuncSetAttribute(ip_fill_staged<M, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
