@@ -3,6 +3,9 @@
 
 #include <atomic>
 #include <thread>
+#if defined(__SSE2__) || defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "common.cuh"
 
@@ -16,6 +19,46 @@ int xfer_workers()
     const unsigned hc = std::thread::hardware_concurrency();
     return hc >= 32 ? 8 : hc >= 8 ? 4 : hc >= 4 ? 2 : 1;
 }
+// Row copies of the staging pipeline.  Rows of an image are tens of KB each -- below the size at which glibc's memcpy
+// switches to non-temporal stores -- so a plain memcpy write-allocates every destination line (read for ownership): three
+// memory transfers per byte instead of two, on a path that is bound by the host's memory bandwidth (266 MB of row copies per
+// 4K VectorGenerator render).  Streaming stores (SSE2, baseline x86-64) skip the read.  OFXCV_XFER_NT=0 restores memcpy.
+bool xfer_nt()
+{
+    static const bool v = !(getenv("OFXCV_XFER_NT") && atoi(getenv("OFXCV_XFER_NT")) == 0);
+    return v;
+}
+inline void copy_row(char* dst, const char* src, size_t n)
+{
+#if defined(__SSE2__) || defined(__x86_64__)
+    if (n >= 4096 && xfer_nt()) {
+        const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+        if (head) {
+            memcpy(dst, src, head);
+            dst += head; src += head; n -= head;
+        }
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+            const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 32)), d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+            _mm_stream_si128((__m128i*)(dst + i), a);
+            _mm_stream_si128((__m128i*)(dst + i + 16), b);
+            _mm_stream_si128((__m128i*)(dst + i + 32), c);
+            _mm_stream_si128((__m128i*)(dst + i + 48), d);
+        }
+        if (i < n) memcpy(dst + i, src + i, n - i);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
+inline void copy_fence()
+{
+#if defined(__SSE2__) || defined(__x86_64__)
+    _mm_sfence();  // streaming stores become visible (to the DMA engine, to the caller's threads) before the chunk is handed on
+#endif
+}
+
 // runs work() on up to n threads; a thread that cannot be created is replaced by the calling thread doing the work
 template <class F>
 void run_workers(int n, F&& work, std::vector<std::thread>& th)
@@ -482,7 +525,8 @@ int ofxcv_upload_rows(ofxcv_ctx* ctx, ofxcv_stream s_, void* dst_dev, const void
             if (k >= nch) return;
             int y0, y1;
             rows_of(k, y0, y1);
-            for (int y = y0; y < y1; y++) memcpy(pinned + (size_t)y * row_bytes, src + (ptrdiff_t)y * src_stride, row_bytes);
+            for (int y = y0; y < y1; y++) copy_row(pinned + (size_t)y * row_bytes, src + (ptrdiff_t)y * src_stride, row_bytes);
+            copy_fence();
             done[k].store(1, std::memory_order_release);
         }
     };
@@ -555,8 +599,9 @@ int ofxcv_download_rows(ofxcv_ctx* ctx, ofxcv_stream s_, void* dst_host, ptrdiff
             }
             int y0, y1;
             rows_of(k, y0, y1);
-            for (int y = y0; y < y1; y++) memcpy(dst + (ptrdiff_t)y * dst_stride, pinned + (size_t)y * row_bytes, row_bytes);
+            for (int y = y0; y < y1; y++) copy_row(dst + (ptrdiff_t)y * dst_stride, pinned + (size_t)y * row_bytes, row_bytes);
         }
+        copy_fence();
     };
     std::vector<std::thread> th;
     if (nch > 1) run_workers(xfer_workers() - 1, work, th);
