@@ -755,7 +755,7 @@ def bench_plugin_boundary(pkg, synth, ctx, W, H):
         best["passes_ms_per_render"] = [round(r["ms_per_render"], 3) for r in passes]
         return best
 
-    a = best_of(3, True, False)
+    a = best_of(5, True, False)
     a.update({"h2d_bytes_per_render": W * H * 16, "d2h_bytes_per_render": W * H * 16,
               "what": "VectorGenerator.ofx, %dx%d float RGBA clips in pageable host memory, default parameters (forward AND backward flow = two "
                       "pairs per render), images labelled by the host (kOfxImagePropUniqueIdentifier): the staged gray frames of the "
@@ -765,7 +765,7 @@ def bench_plugin_boundary(pkg, synth, ctx, W, H):
     b.update({"h2d_bytes_per_render": 3 * W * H * 16, "d2h_bytes_per_render": W * H * 16,
               "what": "the same with a host that does not label its images: all three frames are uploaded and converted every render"})
     out["vectorgenerator_host_clips_unlabelled"] = b
-    c = best_of(2, True, True)
+    c = best_of(3, True, True)
     c.update({"h2d_bytes_per_render": 0, "d2h_bytes_per_render": 0,
               "what": "the same with kOfxImageEffectPropCudaEnabled clips (device pointers): no staging copies"})
     out["vectorgenerator_cuda_clips"] = c

@@ -1524,13 +1524,13 @@ ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* _
 }
 
 // dependency counts of the ready-queue fill: dep[tk] = number of earlier-filled hole pixels in the (2r+3)^2 box of the
-// pixel with fill index tk; pixels without any go straight into the ready queue
-// Also counts the pixels whose latest dependency is one of the 64 tickets right before them (`near`): when that is most
-// of the mask, the fill order lays the dependency chains out one after the other (lines, blobs) and in-order tickets
-// would serialise them.
+// pixel with fill index tk; pixels without any go straight into the ready queue.
+// Also marks the tickets whose LATEST dependency is the ticket right before them (seq[tk]): a run of such tickets is a
+// dependency chain laid out contiguously in the fill order, which in-order tickets can only walk one step at a time (the
+// window of resident warps then covers one chain instead of many).
 __global__ void __launch_bounds__(256) ip_deps(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __restrict__ fidx,
                                                int32_t* __restrict__ dep, int32_t* __restrict__ rq, unsigned* __restrict__ rtail,
-                                               unsigned* __restrict__ near, int range, IpGeom g)
+                                               uint8_t* __restrict__ seq, int range, IpGeom g)
 {
     const unsigned tk = blockIdx.x * blockDim.x + threadIdx.x;
     if (tk >= nfill) return;
@@ -1547,9 +1547,21 @@ __global__ void __launch_bounds__(256) ip_deps(const uint32_t* __restrict__ orde
         }
     dep[tk] = count;
     if (count == 0) rq[atomicAdd(rtail, 1u)] = id;
-    const bool is_near = latest >= 0 && (int)tk - latest <= 64;
-    const unsigned nb = __ballot_sync(__activemask(), is_near);
-    if (is_near && (threadIdx.x & 31) == (unsigned)(__ffs(nb) - 1)) atomicAdd(near, (unsigned)__popc(nb));
+    seq[tk] = latest >= 0 && latest == (int)tk - 1;
+}
+
+// number of tickets inside sequential runs and number of runs (a run starts where seq turns on)
+__global__ void __launch_bounds__(256) ip_runs(const uint8_t* __restrict__ seq, unsigned nfill, unsigned* __restrict__ nseq,
+                                               unsigned* __restrict__ nruns)
+{
+    const unsigned tk = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = tk < nfill && seq[tk];
+    const bool start = in && (tk == 0 || !seq[tk - 1]);
+    const unsigned mi = __ballot_sync(0xffffffffu, in), ms = __ballot_sync(0xffffffffu, start);
+    if ((threadIdx.x & 31) == 0) {
+        if (mi) atomicAdd(nseq, (unsigned)__popc(mi));
+        if (ms) atomicAdd(nruns, (unsigned)__popc(ms));
+    }
 }
 
 struct IpCounters {
@@ -1730,12 +1742,20 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
             OFXCV_CUDA(ctx, cudaMemsetAsync(rq, 0xff, (size_t)nfilled * 4, s));
             OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->pending, 0, sizeof(unsigned), s));
             OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->n_new, 0, sizeof(unsigned), s));
-            ip_deps<<<ofxcv_div_up((int)nfilled, 256), 256, 0, s>>>(order, nfilled, fidx, dep, rq, &ctr->pending, &ctr->n_new, range, g);
+            OFXCV_CUDA(ctx, cudaMemsetAsync(&ctr->pad[0], 0, sizeof(unsigned), s));
+            ip_deps<<<ofxcv_div_up((int)nfilled, 256), 256, 0, s>>>(order, nfilled, fidx, dep, rq, &ctr->pending, tmp, range, g);
+            OFXCV_LAUNCH_CHECK(ctx);
+            ip_runs<<<ofxcv_div_up((int)nfilled, 256), 256, 0, s>>>(tmp, nfilled, &ctr->n_new, &ctr->pad[0]);
             OFXCV_LAUNCH_CHECK(ctx);
             OFXCV_CUDA(ctx, cudaMemcpyAsync(hctr, ctr, sizeof(IpCounters), cudaMemcpyDeviceToHost, s));
             OFXCV_CUDA(ctx, cudaStreamSynchronize(s));
+            // several long chains laid out one after the other in the fill order (horizontal scratches, bars): the ready
+            // queue advances them side by side at ~7.5 us per step (measured at 4K: 45 lines of 3000 px 24 ms against 94 ms
+            // with in-order tickets).  Everything else -- iid masks, blobs, diagonal scratches, ONE line: chains interleaved
+            // by the fill order, or a single chain -- runs 2-5x faster on the in-order incremental fill (~2 us per step).
+            const unsigned nseq = hctr->n_new, nruns = hctr->pad[0];
             const char* rqenv = getenv("OFXCV_IP_READYQ");
-            ready_queue = rqenv ? *rqenv == '1' : (double)hctr->n_new > 0.7 * (double)nfilled;
+            ready_queue = rqenv ? *rqenv == '1' : (nruns >= 4 && (double)nseq >= 256.0 * (double)nruns);
         }
         const int nbox_pad = ((2 * range + 3) * (2 * range + 3) + 3) & ~3;
         const size_t fill_smem = v2 ? ((size_t)nbox_pad * 8 + 32 * (IP_MAXACC + 1) * 4) * IP_WARPS : 0;
