@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_inpaint_gpu.py -x -q -m gpu 2>&1 | tail -5
