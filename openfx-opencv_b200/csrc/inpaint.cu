@@ -693,7 +693,7 @@ template <int METHOD, int CN, bool READYQ>
 __global__ void __launch_bounds__(IP_WARPS * 32, READYQ ? 2 : 4)  // in-order tickets: the resident-warp count is the window over the chains
 ip_fill_staged(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* __restrict__ fidx, const float* __restrict__ t,
                uint8_t* out, ptrdiff_t ostride, uint8_t* done, int32_t* dep, int32_t* rq, unsigned* __restrict__ ticket,
-               unsigned* __restrict__ rtail, uint32_t* pub, int range, IpGeom g)
+               unsigned* __restrict__ rtail, uint32_t* pub, const uint32_t* __restrict__ orig, int range, IpGeom g)
 {
     constexpr int NACC = METHOD == OFXCV_INPAINT_TELEA ? 4 * CN : 2 * CN;
     extern __shared__ __align__(16) unsigned char ip2_smem[];
@@ -780,9 +780,17 @@ ip_fill_staged(const uint32_t* __restrict__ order, unsigned nfill, const int32_t
             px = 0;
             tv = 0.f;
             if (colour && k >= 1 && l >= 1 && k <= g.H && l <= g.W) {
-                const uint8_t* o = out + (size_t)(k - 1) * ostride + (size_t)(l - 1) * CN;
+                // a hole filled LATER than this pixel is not known, but a tap on the image's border ring reads neighbours
+                // whose flags it did not test (the CPU code's clamped indices): what the CPU sees there is the source colour,
+                // and `out` may already hold what a warp running ahead has written
+                const int f = __ldg(fidx + k * ec + l);
+                if (f > (int)tk && f != 0x7fffffff) {
+                    px = __ldg(orig + f);
+                } else {
+                    const uint8_t* o = out + (size_t)(k - 1) * ostride + (size_t)(l - 1) * CN;
 #pragma unroll
-                for (int c = 0; c < CN; c++) px |= (uint32_t)ld_u8_cg(o + c) << (8 * c);
+                    for (int c = 0; c < CN; c++) px |= (uint32_t)ld_u8_cg(o + c) << (8 * c);
+                }
             }
             if (METHOD == OFXCV_INPAINT_TELEA && k >= 0 && l >= 0 && k < er && l < ec) tv = __ldg(t + k * ec + l);
         };
@@ -1770,12 +1778,12 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
     do {                                                                                                                           \
         if (inc_smem > 48 * 1024)                                                                                                  \
             OFXCV_CUDA(ctx, cudaFuncSetAttribute(ip_fill_inc<M, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inc_smem)); \
-        ip_orig<C><<<ofxcv_div_up((int)nfilled, 256), 256, 0, s>>>(order, nfilled, out, out_stride, orig, g);                      \
         ip_fill_inc<M, C, B><<<blocks, IP_WARPS * 32, inc_smem, s>>>(order, nfilled, fidx, t, out, out_stride, &ctr->ticket, pub,  \
                                                                      orig, range, inc_wait_all, g);                                \
     } while (0)
 #define IP_FILL(M, C)                                                                                                              \
     do {                                                                                                                           \
+        if (v2) ip_orig<C><<<ofxcv_div_up((int)nfilled, 256), 256, 0, s>>>(order, nfilled, out, out_stride, orig, g);              \
         if (inc) {                                                                                                                 \
             IP_FILL_INC(M, C, 3);                                                                                                  \
         } else if (v2) {                                                                                                              \
@@ -1788,11 +1796,11 @@ int ofxcv_inpaint_u8(ofxcv_ctx* ctx, ofxcv_stream stream_, const uint8_t* img, p
             if (ready_queue)                                                                                                       \
                 ip_fill_staged<M, C, true><<<blocks, IP_WARPS * 32, fill_smem, s>>>(order, nfilled, fidx, t, out, out_stride,     \
                                                                                     done, dep, rq, &ctr->ticket, &ctr->pending,   \
-                                                                                    pub, range, g);                                \
+                                                                                    pub, orig, range, g);                          \
             else                                                                                                                   \
                 ip_fill_staged<M, C, false><<<blocks, IP_WARPS * 32, fill_smem, s>>>(order, nfilled, fidx, t, out, out_stride,    \
                                                                                      done, dep, rq, &ctr->ticket, &ctr->pending,  \
-                                                                                     pub, range, g);                               \
+                                                                                     pub, orig, range, g);                         \
         } else {                                                                                                                   \
             ip_fill<M, C><<<blocks, IP_WARPS * 32, 0, s>>>(order, nfilled, (uint32_t)g.np, hole, cnt, t, out, out_stride, done,    \
                                                            &ctr->ticket, range, g);                                                \

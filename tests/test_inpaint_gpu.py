@@ -199,15 +199,16 @@ def test_inpaint_mask_shapes_both_schedulers(ctx, oracle, synth, method, cn):
             assert nbad == 0, "%s: %d differing bytes (method %d, cn %d, r %d)" % (name, nbad, method, cn, radius)
 
 
+@pytest.mark.parametrize("radius", [3, 5])
 @pytest.mark.parametrize("method", [TELEA, NS])
-def test_inpaint_in_place(ctx, oracle, synth, method):
+def test_inpaint_in_place(ctx, oracle, synth, method, radius):
     """out == img: the fill must not depend on what a warp running ahead has already written into the image."""
     h, w = 200, 300
     img = synth.texture(h, w, 5)
     mask = synth.iid_mask(h, w, 6, 0.25)
     mask[0, :] = 255          # a whole border row of holes: taps on row 1 read it through clamped indices
     d_img, d_mask = ctx.to_device(img), ctx.to_device(mask)
-    ctx.inpaint_dev(d_img.ptr, 3, d_mask.ptr, d_img.ptr, w, h, 3.0, method)
+    ctx.inpaint_dev(d_img.ptr, 3, d_mask.ptr, d_img.ptr, w, h, float(radius), method)
     ctx.synchronize()
     got = d_img.download((h, w, 3), np.uint8)
-    assert int((got != oracle.inpaint(img, mask, 3, method)).sum()) == 0
+    assert int((got != oracle.inpaint(img, mask, radius, method)).sum()) == 0
