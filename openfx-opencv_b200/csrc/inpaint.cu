@@ -1361,6 +1361,10 @@ ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* _
                     }
             }
         };
+        // Telea: the weight of a tap (two f64 divisions and an f64 square root) depends on T and the geometry only, never on
+        // a colour: the first round computes it for EVERY contributing tap, also for those whose colours are still held back
+        // (list entry bit 31 = "weight only"), and parks it in the spare column of the term table
+        bool first_round = true;
         for (;;) {
             // hand every tap with nothing pending around it to a lane
             int total = 0;
@@ -1371,10 +1375,12 @@ ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* _
                     const uint4 a = aff[u * 32 + lane];
                     r = ((a.x & P[0]) | (a.y & P[1]) | (a.z & P[2]) | (a.w & P[3])) == 0u;
                 }
-                const unsigned m = __ballot_sync(FULL, r);
-                if (r) {
-                    s_list[total + __popc(m & lt)] = (uint32_t)(u * 32 + lane) | ((uint32_t)(tdk[u] + 64) << 8) | ((uint32_t)(tdl[u] + 64) << 16);
-                    todo[u] = false;
+                const bool sub = r || (METHOD == OFXCV_INPAINT_TELEA && first_round && todo[u]);
+                const unsigned m = __ballot_sync(FULL, sub);
+                if (sub) {
+                    s_list[total + __popc(m & lt)] = (uint32_t)(u * 32 + lane) | ((uint32_t)(tdk[u] + 64) << 8) | ((uint32_t)(tdl[u] + 64) << 16) |
+                                                     (r ? 0u : 0x80000000u);
+                    if (r) todo[u] = false;
                 }
                 total += __popc(m);
             }
@@ -1383,6 +1389,7 @@ ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* _
                 if (base + lane < total) {
                     const uint32_t e = s_list[base + lane];
                     const int tp = (int)(e & 0xffu), dk = (int)((e >> 8) & 0xffu) - 64, dl = (int)((e >> 16) & 0xffu) - 64;
+                    const bool weight_only = (e >> 31) != 0;
                     const int k = i + dk, l = j + dl;
                     float term[IP_MAXACC];
                     const int km = k - 1 + (k == 1), kp = k - 1 - (k == er - 2);
@@ -1390,12 +1397,19 @@ ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* _
                     const bool fr = known(k, l + 1), fl = known(k, l - 1), fd = known(k + 1, l), fu = known(k - 1, l);
                     if (METHOD == OFXCV_INPAINT_TELEA) {
                         float ry = (float)(i - k), rx = (float)(j - l);
-                        float vl = rx * rx + ry * ry;
-                        float dst = (float)(1. / (vl * sqrt((double)vl)));
-                        float lev = (float)(1. / (1 + (double)fabsf(TV(k, l) - ti)));  // f32 difference, f64 sum (C fabs)
-                        float dir = rx * gTx + ry * gTy;
-                        if (fabs(dir) <= 0.01) dir = 0.000001f;
-                        float w = (float)fabs(dst * lev * dir);
+                        float w;
+                        if (first_round) {
+                            float vl = rx * rx + ry * ry;
+                            float dst = (float)(1. / (vl * sqrt((double)vl)));
+                            float lev = (float)(1. / (1 + (double)fabsf(TV(k, l) - ti)));  // f32 difference, f64 sum (C fabs)
+                            float dir = rx * gTx + ry * gTy;
+                            if (fabs(dir) <= 0.01) dir = 0.000001f;
+                            w = (float)fabs(dst * lev * dir);
+                            s_term[tp][IP_MAXACC] = w;
+                        } else {
+                            w = s_term[tp][IP_MAXACC];
+                        }
+                        if (!weight_only) {
 #pragma unroll
                         for (int c = 0; c < CN; c++) {
                             float gIx, gIy;
@@ -1417,6 +1431,7 @@ ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* _
                             term[c * 4 + 1] = -(w * (gIx * rx));
                             term[c * 4 + 2] = -(w * (gIy * ry));
                             term[c * 4 + 3] = w;
+                        }
                         }
                     } else {
                         float ry = (float)(k - i), rx = (float)(l - j);
@@ -1448,11 +1463,14 @@ ip_fill_inc(const uint32_t* __restrict__ order, unsigned nfill, const int32_t* _
                             term[c * 2 + 1] = w;
                         }
                     }
+                    if (!weight_only) {
 #pragma unroll
-                    for (int a = 0; a < NACC; a++) s_term[tp][a] = term[a];
+                        for (int a = 0; a < NACC; a++) s_term[tp][a] = term[a];
+                    }
                 }
             }
             __syncwarp();
+            first_round = false;
             if ((P[0] | P[1] | P[2] | P[3]) == 0u) break;  // nothing was pending: that round was the last
             // poll the pending words until some have arrived, stage them, release the taps around them
             uint32_t pv[IP2_NPOS];
