@@ -15,6 +15,9 @@ img = s.texture(60, 80, 1)
 for m in (p.INPAINT_NS, p.INPAINT_TELEA):
     ctx.inpaint(img, s.iid_mask(60, 80, 2, 0.1), 3, m)
     ctx.inpaint(img, s.blob_mask(60, 80, 3), 5, m)
+    ctx.inpaint(img, s.iid_mask(60, 80, 4, 0.3), 4, m)                  # incremental fill, three tap rounds
+    lines = np.zeros((120, 400), np.uint8); lines[10:110:9, 20:380] = 255  # chains laid out back to back: the ready-queue fill
+    ctx.inpaint(s.texture(120, 400, 2), lines, 3, m)
 ctx.watershed(img, s.seed_markers(60, 80, 5, 5))                       # one frame: the round-synchronous parallel flood
 noise = np.random.default_rng(9).integers(0, 256, (70, 90, 3), dtype=np.uint8)
 ctx.watershed(noise, s.seed_markers(70, 90, 6, 3))                    # levels above 32: the 256-level instantiation
