@@ -68,3 +68,27 @@ def seed_markers(h, w, n, seed, r=2):
     for i, (y, x) in enumerate(zip(ys, xs)):
         mk[y - r:y + r + 1, x - r:x + r + 1] = i + 1
     return mk
+
+
+def shape_masks(h, w):
+    """Masks whose fill order differs in kind: chains laid out back to back (horizontal lines: the ready-queue fill),
+    chains interleaved by the fill order (diagonal scratches, a thick bar: the in-order incremental fill)."""
+    lines = np.zeros((h, w), np.uint8)
+    lines[20:h - 20:12, 15:w - 15] = 255
+    thick = np.zeros((h, w), np.uint8)
+    thick[h // 2 - 4:h // 2 + 5, 10:w - 10] = 255
+    diag = np.zeros((h, w), np.uint8)
+    rng = np.random.default_rng(11)
+    for _ in range(14):
+        x0, y0, n, sl = int(rng.integers(5, w // 2)), int(rng.integers(10, h - 10)), int(rng.integers(40, w // 2 - 10)), rng.uniform(-0.8, 0.8)
+        for t in range(n):
+            yy = min(max(int(y0 + sl * t), 0), h - 2)
+            diag[yy:yy + 2, x0 + t] = 255
+    edge = np.zeros((h, w), np.uint8)   # holes on the image's border ring and next to it: the clamped-index reads of the CPU code
+    edge[0, ::3] = 255
+    edge[1, 1::4] = 255
+    edge[h - 1, ::2] = 255
+    edge[:, 0] = 255
+    edge[2:h - 2:5, w - 1] = 255
+    edge[2:h - 2:7, w - 2] = 255
+    return {"lines": lines, "thick": thick, "diag": diag, "edge": edge}

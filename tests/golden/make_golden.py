@@ -51,6 +51,23 @@ def inpaint():
     np.savez_compressed(os.path.join(HERE, "inpaint_cv2.npz"), **out)
 
 
+def inpaint_shapes():
+    """Masks whose fill order differs in kind (synth.shape_masks): chains laid out back to back, interleaved chains,
+    holes on the image's border ring (the clamped-index reads of cv::inpaint)."""
+    out = {}
+    h, w = 96, 128
+    rgb = synth.texture(h, w, 9)
+    out["rgb"] = rgb
+    for mname, m in synth.shape_masks(h, w).items():
+        out["mask_" + mname] = m
+        for cn in (1, 3):
+            img = rgb if cn == 3 else synth.gray(rgb)
+            for r in (3, 4):
+                for meth, flag in (("telea", cv2.INPAINT_TELEA), ("ns", cv2.INPAINT_NS)):
+                    out["out_%s_c%d_r%d_%s" % (mname, cn, r, meth)] = cv2.inpaint(img, m, r, flag)
+    np.savez_compressed(os.path.join(HERE, "inpaint_shapes_cv2.npz"), **out)
+
+
 def watershed():
     out = {}
     for name, (h, w, n, seed) in {"a": (120, 160, 9, 5), "b": (64, 64, 4, 2)}.items():
@@ -115,7 +132,7 @@ def lut():
 
 if __name__ == "__main__":
     print("cv2", cv2.__version__)
-    farneback(); inpaint(); watershed(); lut(); tvl1_primitives()
+    farneback(); inpaint(); inpaint_shapes(); watershed(); lut(); tvl1_primitives()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

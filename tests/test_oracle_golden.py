@@ -23,6 +23,26 @@ def test_inpaint_bit_exact(oracle, synth):
     assert n == 48
 
 
+def test_inpaint_mask_shapes_bit_exact(oracle, synth):
+    """cv2 outputs on masks whose fill order differs in kind (lines, a bar, diagonal scratches) and on holes on the image's
+    border ring, where cv::inpaint reads neighbours through clamped indices (what the GPU fill's source-colour table serves)."""
+    z = np.load(os.path.join(G, "inpaint_shapes_cv2.npz"))
+    rgb = z["rgb"]
+    h, w = rgb.shape[:2]
+    masks = synth.shape_masks(h, w)
+    n = 0
+    for key in z.files:
+        if not key.startswith("out_"):
+            continue
+        _, mname, c, r, meth = key.split("_")
+        assert np.array_equal(masks[mname], z["mask_" + mname]), mname   # the GPU tests use the same generator
+        img = rgb if c == "c3" else synth.gray(rgb)
+        got = oracle.inpaint(img, z["mask_" + mname], float(r[1:]), 1 if meth == "telea" else 0)
+        assert np.array_equal(got, z[key]), key
+        n += 1
+    assert n == 32
+
+
 def test_watershed_bit_exact(oracle):
     z = np.load(os.path.join(G, "watershed_cv2.npz"))
     for name in ("a", "b", "noise"):
