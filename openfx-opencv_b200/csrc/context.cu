@@ -592,10 +592,10 @@ int ofxcv_download_rows(ofxcv_ctx* ctx, ofxcv_stream s_, void* dst_host, ptrdiff
         cudaSetDevice(device);
         for (;;) {
             const int k = next.fetch_add(1);
-            if (k >= nch) return;
+            if (k >= nch) break;
             if (cudaEventSynchronize(ctx->xfer_ev[k]) != cudaSuccess) {
                 failed.store(1);
-                return;
+                break;
             }
             int y0, y1;
             rows_of(k, y0, y1);
