@@ -23,7 +23,9 @@ sequence is periodic with the block length), so the per-output checksums of all 
              output inside the timed region, every step;
   e2e_plugin (farneback_4k, N=1) = the same through the drop-in .ofx bundle itself: the mini-host drives
              kOfxImageEffectActionRender of VectorGenerator.ofx over a 4K clip of host float RGBA images (a default render is
-             TWO pairs: forward and backward flow), plus the inpaint / segment bundles on RGBA8 frames;
+             TWO pairs: forward and backward flow), plus the inpaint / segment bundles on RGBA8 frames.  Measured first, in
+             a process of its own (idle GPU and host cores: one render at a time is a latency measurement); the boxes are
+             shared, so every pass over the clip is listed and the fastest pass's median is the figure;
   roofline = the dominant kernel: algorithmic bytes per launch / its average CUDA-event duration inside a timed pass,
              against the measured HBM copy peak in MEASURED_PEAKS.json (fallback 6650 GB/s); `traffic` = dram bytes
              read+written per launch from the newest committed `ncu --set full` summary (profiles/*_ncu_fb_band3.json);
